@@ -1,0 +1,171 @@
+/* tfusion_b200 — C ABI of the B200-native per-frame dense-reconstruction hot path.
+ *
+ * This is the boundary a maintainer of 3d-scan/topfusion binds instead of the reference's
+ * internal host->device seam.  Every entry point names the reference interface it replaces
+ * (paths relative to /root/reference/tfusion).  Plain pointers and sizes only; no torch,
+ * OpenCV or C++ types.  All functions return TFB_OK (0) or a negative tfb_status and never
+ * call exit() (the reference prints and exits: src/safe_call.hpp:13-27,
+ * include/tfusion/cuda/CUDADefines.hpp:22-33).  A context is not thread-safe (neither is
+ * the reference).  There is NO CPU fallback: without a CUDA device tfb_create fails.
+ *
+ * Conventions
+ *   - images are dense row-major device buffers (no pitch)
+ *   - points / normals are float4 per pixel (x,y,z,w), NaN x marks an invalid pixel
+ *   - poses are row-major float[16] (the storage of cv::Affine3f::matrix.val), metres
+ *   - "pose_w2c" = world->camera, "pose_c2w" = camera->world (TopFu::poses_ are c2w)
+ */
+#ifndef TFUSION_B200_H
+#define TFUSION_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define TFB_API __attribute__((visibility("default")))
+#else
+#define TFB_API
+#endif
+
+typedef enum tfb_status {
+    TFB_OK = 0,
+    TFB_ERR_ARG = -1,    /* null pointer, bad size, unsupported parameter */
+    TFB_ERR_CUDA = -2,   /* a CUDA call failed; see tfb_last_error */
+    TFB_ERR_NOMEM = -3,
+    TFB_ERR_STATE = -4   /* call not valid in the current state */
+} tfb_status;
+
+/* TopFuParams + SceneParams (src/topfu.cpp:12-53, include/tfusion/SceneParams.hpp:45-53) and
+ * the hash geometry the reference fixes at compile time (include/tfusion/cuda/VoxelBlockHash.hpp:10-18),
+ * here run-time so the 2M-block / 2 mm configurations fit. */
+typedef struct tfb_params {
+    int32_t cols, rows;             /* rows % 8 == 0 and cols % 8 == 0 */
+    float fx, fy, cx, cy;
+    float bilateral_sigma_depth;    /* metres */
+    float bilateral_sigma_spatial;  /* pixels */
+    int32_t bilateral_kernel_size;  /* odd, <= 15 */
+    float icp_truncate_depth_dist;  /* metres; <= 0 disables (topfu.cpp:190-191) */
+    float icp_dist_thres;           /* metres */
+    float icp_angle_thres;          /* radians */
+    int32_t icp_iters[4];           /* iterations for pyramid level 0..3 (topfu.cpp:14) */
+    float mu;                       /* truncation band, metres */
+    int32_t max_w;
+    float voxel_size;               /* metres */
+    float view_frustum_min, view_frustum_max;
+    int32_t stop_integrating_at_max_w;
+    int32_t num_blocks;             /* SDF_LOCAL_BLOCK_NUM  (0x10000) */
+    int32_t num_buckets;            /* SDF_BUCKET_NUM, power of two (0x100000) */
+    int32_t excess_size;            /* SDF_EXCESS_LIST_SIZE (0x20000) */
+    int32_t depth_cutoff_mm;        /* src/cuda/imgproc.cu:277 hard-codes 2047 */
+    int32_t corrected_mode;         /* 0: reference behaviour incl. SURVEY.md F1; 1: model maps in the camera frame */
+    int32_t shard_rank, shard_count;/* voxel payload sharded by block coordinate; index replicated */
+} tfb_params;
+
+typedef struct tfb_ctx tfb_ctx;
+
+/* ---- life cycle ------------------------------------------------------------------------ */
+/* TopFuParams::default_params(), src/topfu.cpp:12-53 */
+TFB_API int tfb_default_params(tfb_params* p);
+/* TopFu::TopFu, src/topfu.cpp:55-84 (scene, engines, render state, ICP, buffers, reset).
+ * stream: a cudaStream_t to run on, or NULL to let the context create its own non-blocking stream. */
+TFB_API int tfb_create(const tfb_params* p, void* stream, tfb_ctx** out);
+TFB_API int tfb_destroy(tfb_ctx* c);
+/* TopFu::reset, src/topfu.cpp:141-152 -> ResetScene, src/cuda/SceneReconstructionEngine_host.cu:52-73 */
+TFB_API int tfb_reset(tfb_ctx* c);
+TFB_API const char* tfb_last_error(const tfb_ctx* c);
+TFB_API const char* tfb_version(void);
+
+/* ---- raw device memory helpers (cuda::DeviceMemory, src/device_memory.cpp:46-135) ------- */
+TFB_API int tfb_dev_alloc(void** dptr, size_t bytes);
+TFB_API int tfb_dev_free(void* dptr);
+TFB_API int tfb_host_alloc_pinned(void** hptr, size_t bytes);
+TFB_API int tfb_host_free_pinned(void* hptr);
+TFB_API int tfb_h2d(tfb_ctx* c, void* dst_dev, const void* src_host, size_t bytes);  /* async on the context stream */
+TFB_API int tfb_d2h(tfb_ctx* c, void* dst_host, const void* src_dev, size_t bytes);  /* waits for the stream */
+TFB_API int tfb_sync(tfb_ctx* c);                                                    /* cuda::waitAllDefaultStream */
+
+/* ---- image stages: tfusion::device::* declared in src/internal.hpp:122-132 ------------- */
+/* compute_dists, src/cuda/imgproc.cu:263-290 */
+TFB_API int tfb_compute_dists(tfb_ctx* c, const uint16_t* depth, float* dists, int cols, int rows);
+/* bilateralFilter, imgproc.cu:10-61 */
+TFB_API int tfb_bilateral_filter(tfb_ctx* c, const uint16_t* src, uint16_t* dst, int cols, int rows,
+                                 int kernel_size, float sigma_spatial, float sigma_depth);
+/* truncateDepth, imgproc.cu:70-89 */
+TFB_API int tfb_truncate_depth(tfb_ctx* c, uint16_t* depth, int cols, int rows, float max_dist);
+/* depthPyr, imgproc.cu:98-140; dst is (src_cols/2, src_rows/2) */
+TFB_API int tfb_depth_pyr(tfb_ctx* c, const uint16_t* src, uint16_t* dst, int src_cols, int src_rows, float sigma_depth);
+/* computePointNormals, imgproc.cu:214-254 */
+TFB_API int tfb_compute_point_normals(tfb_ctx* c, const uint16_t* depth, float* points, float* normals,
+                                      int cols, int rows, float fx, float fy, float cx, float cy);
+/* resizePointsNormals, imgproc.cu:355-401 */
+TFB_API int tfb_resize_points_normals(tfb_ctx* c, const float* points, const float* normals,
+                                      float* points_out, float* normals_out, int src_cols, int src_rows);
+/* the fused form the frame path uses: dists + bilateral + truncate + pyramid + maps for all used levels,
+ * written into the context's current-frame buffers (src/topfu.cpp:166-197) */
+TFB_API int tfb_preprocess(tfb_ctx* c, const uint16_t* depth_dev);
+
+/* ---- ICP: ComputeIcpHelper::operator() src/cuda/proj_icp.cu:432-455, StreamHelper::get and
+ *      ProjectiveICP::estimateTransform src/projective_icp.cpp:43-62,169-212 ---------------- */
+/* one reduction for a fixed transform: 27 sums in the reference's packed order A00..A05,b0,A11..b5 */
+TFB_API int tfb_icp_reduce(tfb_ctx* c, int cols, int rows, float fx, float fy, float cx, float cy,
+                           const float aff[16], const float* vcurr, const float* ncurr,
+                           const float* vprev, const float* nprev, float out27_host[27]);
+/* the whole coarse-to-fine loop on the context's current / model pyramids; solve on the device */
+TFB_API int tfb_icp_estimate(tfb_ctx* c, float affine_out[16], int* ok);
+
+/* ---- scene engine: SceneReconstructionEngine_CUDA, include/tfusion/cuda/SceneReconstructionEngine_host.hpp:52-57 */
+/* AllocateSceneFromDepth, src/cuda/SceneReconstructionEngine_host.cu:76-195 */
+TFB_API int tfb_allocate_scene_from_depth(tfb_ctx* c, const float pose_w2c[16], const float* dists_dev);
+/* IntegrateIntoScene, SceneReconstructionEngine_host.cu:198-251 */
+TFB_API int tfb_integrate_into_scene(tfb_ctx* c, const float pose_w2c[16], const float* dists_dev);
+
+/* ---- visualisation engine: VisualisationEngine_CUDA, include/tfusion/cuda/VisualisationEngine_CUDA.hpp:38-45 */
+/* CreateExpectedDepths, src/cuda/VisualisationEngine_CUDA.cu:120-173 */
+TFB_API int tfb_create_expected_depths(tfb_ctx* c, const float pose_w2c[16]);
+/* CreateICPMaps, VisualisationEngine_CUDA.cu:324-360,474-493: raycast (updates the visible set) + model maps */
+TFB_API int tfb_create_icp_maps(tfb_ctx* c, const float pose_c2w[16], float* points_dev, float* normals_dev);
+
+/* ---- the frame: TopFu::operator(), src/topfu.cpp:161-330 ------------------------------- */
+/* depth_host: rows x cols u16 millimetres with row stride step_bytes (cv::Mat data/step; pinned memory
+ * makes the upload asynchronous).  *ok receives operator()'s return value. */
+TFB_API int tfb_process_frame(tfb_ctx* c, const uint16_t* depth_host, size_t step_bytes, int* ok);
+/* same with the frame already on the device, dense (cuda::Depth after upload, apps/demo.cpp:100-104) */
+TFB_API int tfb_process_frame_device(tfb_ctx* c, const uint16_t* depth_dev, int* ok);
+/* TopFu::getCameraPose, src/topfu.cpp:154-159 */
+TFB_API int tfb_get_pose(const tfb_ctx* c, int time, float out16[16]);
+TFB_API int tfb_num_poses(const tfb_ctx* c);
+
+/* ---- inspection (tests, bench, debug dumps) ---------------------------------------------- */
+/* out[8] = n_visible, last_free_block, last_free_excess, n_new_this_frame, frame_counter, resets,
+ *          n_raycast_extras, n_allocated */
+TFB_API int tfb_get_counters(tfb_ctx* c, long long out[8]);
+TFB_API long long tfb_voxel_updates_last(tfb_ctx* c);   /* 512 x visible entries with ptr >= 0 */
+TFB_API int tfb_total_entries(const tfb_ctx* c);
+TFB_API int tfb_export_table(tfb_ctx* c, void* host_entries);       /* total_entries x 16 B HashEntry */
+TFB_API int tfb_export_vis_type(tfb_ctx* c, uint8_t* host);         /* total_entries */
+TFB_API int tfb_export_visible_ids(tfb_ctx* c, int32_t* host, int capacity, int* n);
+TFB_API int tfb_export_block(tfb_ctx* c, int ptr, void* host512x4); /* one block: 512 x {i16 sdf, u8 w, u8 pad} */
+TFB_API int tfb_export_minmax(tfb_ctx* c, float* host);             /* (rows/8) x (cols/8) x 2 */
+TFB_API int tfb_export_raycast(tfb_ctx* c, float* host);            /* rows x cols x 4, voxel units */
+TFB_API int tfb_export_dists(tfb_ctx* c, float* host);
+/* which: 0 current depth (u16), 1 current points, 2 current normals, 3 model points, 4 model normals */
+TFB_API int tfb_export_level(tfb_ctx* c, int which, int level, void* host);
+TFB_API int tfb_import_level(tfb_ctx* c, int which, int level, const void* host);
+/* device pointers of the context's own buffers (same `which` codes; 5 = dists) */
+TFB_API void* tfb_level_ptr(tfb_ctx* c, int which, int level);
+
+/* ---- timing on the context stream (CUDA events) -------------------------------------------
+ * stage ids: 0 upload, 1 preprocess, 2 icp, 3 allocate, 4 integrate, 5 expected depth,
+ *            6 raycast + icp maps, 7 map pyramid, 8 whole frame */
+TFB_API int tfb_timing_enable(tfb_ctx* c, int on);
+TFB_API int tfb_timing_last_ms(tfb_ctx* c, float out9[9]);
+/* number of kernels this library launched since the context was created */
+TFB_API long long tfb_kernel_launches(const tfb_ctx* c);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TFUSION_B200_H */

@@ -1,0 +1,97 @@
+"""GPU parity — projective ICP (src/cuda/proj_icp.cu, src/projective_icp.cpp).  Floating point with a
+different (but fixed) summation order: fp32 shuffle partials + fp64 final fold here, fp32 256-wide trees in the
+reference.  Tolerances: 27-vector 2e-4 relative to the largest |term| of its kind; transform 1e-4 m / 1e-4 rad
+(the north-star pose tolerance)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _rot_angle(Ra, Rb):
+    """angle of Ra^T Rb from its skew part (arccos of the trace has a 5e-4 noise floor on fp32 rotations)"""
+    D = Ra.astype(np.float64).T @ Rb.astype(np.float64)
+    w = 0.5 * np.array([D[2, 1] - D[1, 2], D[0, 2] - D[2, 0], D[1, 0] - D[0, 1]])
+    return float(np.arcsin(min(1.0, np.linalg.norm(w))))
+
+
+@pytest.fixture(scope="module")
+def maps(oracle_lib, s0_frames):
+    depth, _, intr = s0_frames
+    def prep(d):
+        d0 = oracle_lib.truncate_depth(oracle_lib.bilateral(d), 2.0)
+        return oracle_lib.points_normals(d0, intr)
+    return prep(depth[0]), prep(depth[6]), intr
+
+
+def test_reduction_matches_for_fixed_transforms(gpu, oracle_lib, maps):
+    (vp, np_), (vc, nc), intr = maps
+    c = gpu.Context()
+    try:
+        # At the identity every current point projects exactly onto its own pixel centre, so the point-sampled
+        # texel floor(coo) flips with the last bit of __fdividef (device) vs IEEE division (oracle): a knife edge
+        # of the reference's own design, hence the looser bound there.
+        cases = ((np.eye(4, dtype=np.float32), 2e-3),
+                 (oracle_lib.rodrigues([0.002, -0.003, 0.001], [0.004, -0.002, 0.003]), 5e-4))
+        for aff, tol in cases:
+            o27, ncorr = oracle_lib.icp_reduce(intr, aff, vc, nc, vp, np_)
+            g27 = c.icp_reduce(intr, aff, vc, nc, vp, np_)
+            assert ncorr > 100000
+            scale = np.abs(o27).max()
+            assert np.abs(g27 - o27).max() <= tol * scale, (np.abs(g27 - o27).max(), scale)
+    finally:
+        c.close()
+
+
+def test_reduction_no_correspondences_is_zero(gpu, oracle_lib, maps):
+    (vp, np_), (vc, nc), intr = maps
+    c = gpu.Context()
+    try:
+        far = np.eye(4, dtype=np.float32); far[2, 3] = 5.0   # push everything 5 m away: nothing within 0.1 m
+        g27 = c.icp_reduce(intr, far, vc, nc, vp, np_)
+        o27, n = oracle_lib.icp_reduce(intr, far, vc, nc, vp, np_)
+        assert n == 0 and not o27.any() and not g27.any()
+        nan = np.full_like(vc, np.nan)
+        assert not c.icp_reduce(intr, np.eye(4, dtype=np.float32), nan, nan, vp, np_).any()
+    finally:
+        c.close()
+
+
+def test_estimate_transform_matches_oracle(gpu, s0_frames):
+    from oracle import tfo
+    depth, _, _ = s0_frames
+    o = tfo.Oracle()
+    g = gpu.Context()
+    try:
+        # model maps = frame 0, current = frame 6, installed on both sides through the same path
+        o.preprocess(depth[0]); g.preprocess(depth[0])
+        for lvl in range(3):
+            for w_src, w_dst in ((1, 3), (2, 4)):
+                o.set_level(w_dst, lvl, o.level(w_src, lvl))
+                g.set_level(w_dst, lvl, o.level(w_src, lvl))
+        o.preprocess(depth[6]); g.preprocess(depth[6])
+        ok_o, a_o = o.estimate_transform()
+        ok_g, a_g = g.estimate_transform()
+        assert ok_o and ok_g
+        assert np.abs(a_o[:3, 3] - a_g[:3, 3]).max() < 1e-4
+        assert _rot_angle(a_o[:3, :3], a_g[:3, :3]) < 1e-4
+        assert np.abs(a_o[:3, 3]).max() > 1e-4   # a real motion was estimated
+    finally:
+        g.close(); o.close()
+
+
+def test_tracking_failure_is_reported(gpu, s0_frames):
+    """no correspondences -> A = 0 -> |det| < 1e-15 -> estimateTransform returns false (projective_icp.cpp:197-203)"""
+    depth, _, _ = s0_frames
+    g = gpu.Context()
+    try:
+        g.preprocess(depth[0])           # current maps valid, model maps still all-zero/invalid
+        nan = np.full((480, 640, 4), np.nan, np.float32)
+        g.set_level(3, 0, nan); g.set_level(4, 0, nan)
+        for lvl in (1, 2):
+            n = np.full((480 >> lvl, 640 >> lvl, 4), np.nan, np.float32)
+            g.set_level(3, lvl, n); g.set_level(4, lvl, n)
+        ok, _ = g.estimate_transform()
+        assert not ok
+    finally:
+        g.close()

@@ -1,0 +1,545 @@
+// Context, frame orchestration and the extern "C" boundary declared in include/tfusion_b200.h.
+// The frame path mirrors tfusion::TopFu::operator() (/root/reference/tfusion/src/topfu.cpp:161-330) but
+// enqueues every stage on one stream and waits exactly once, for the 1 KB state block that carries the new
+// pose, the tracking verdict and the counters.  The reference blocks the host 22 times per frame (27 with
+// its debug downloads).
+#include <math.h>
+#include <new>
+#include <stdlib.h>
+
+#include "tfb_common.cuh"
+
+namespace tfb {
+int launch_raycast(tfb_ctx* c, bool update_visible);
+}
+
+using namespace tfb;
+
+namespace {
+
+enum { ST_UPLOAD = 0, ST_PRE, ST_ICP, ST_ALLOC, ST_INTEG, ST_EXPECT, ST_RAYCAST, ST_PYR, ST_FRAME, ST_COUNT };
+
+int used_levels(const tfb_params& p) {  // ProjectiveICP::getUsedLevelsNum, projective_icp.cpp:110-115
+    int i = MAX_LEVELS - 1;
+    for (; i >= 0 && !p.icp_iters[i]; --i) {}
+    return i + 1;
+}
+
+template <typename T>
+cudaError_t dmalloc(T** p, size_t n) { return cudaMalloc((void**)p, n * sizeof(T)); }
+
+void free_all(tfb_ctx* c) {
+    cudaFree(c->table); cudaFree(c->vba); cudaFree(c->vba_free); cudaFree(c->excess_free);
+    cudaFree(c->claim_key); cudaFree(c->claimed); cudaFree(c->vis_type); cudaFree(c->vis_list[0]); cudaFree(c->vis_list[1]);
+    cudaFree(c->minmax); cudaFree(c->raycast); cudaFree(c->dists); cudaFree(c->depth_in); cudaFree(c->icp_partial);
+    cudaFree(c->ds);
+    for (int l = 0; l < MAX_LEVELS; ++l) {
+        cudaFree(c->lv[l].depth); cudaFree(c->lv[l].vcurr); cudaFree(c->lv[l].ncurr); cudaFree(c->lv[l].vprev); cudaFree(c->lv[l].nprev);
+    }
+    if (c->hs) cudaFreeHost(c->hs);
+    if (c->h_pose_stage) cudaFreeHost(c->h_pose_stage);
+    if (c->h_icp27) cudaFreeHost(c->h_icp27);
+    for (int i = 0; i < 16; ++i)
+        if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    free(c->poses);
+}
+
+int push_pose(tfb_ctx* c, const float* m) {
+    if (c->n_poses == c->cap_poses) {
+        int cap = c->cap_poses ? c->cap_poses * 2 : 1024;
+        float* np = (float*)realloc(c->poses, (size_t)cap * 16 * sizeof(float));
+        if (!np) return set_err(c, TFB_ERR_NOMEM, "pose history");
+        c->poses = np; c->cap_poses = cap;
+    }
+    memcpy(c->poses + (size_t)c->n_poses * 16, m, 16 * sizeof(float));
+    c->n_poses++;
+    return TFB_OK;
+}
+
+const float IDENTITY[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+
+int fetch_state(tfb_ctx* c) {
+    TFB_CUDA(c, cudaMemcpyAsync(c->hs, c->ds, sizeof(DevState), cudaMemcpyDeviceToHost, c->stream));
+    TFB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return TFB_OK;
+}
+
+// TopFu::reset (topfu.cpp:141-152): clear poses, push identity, ResetScene.  The render state (visible list,
+// visibility types) is deliberately left alone, as in the reference.
+int do_reset(tfb_ctx* c) {
+    if (c->frame_counter) c->resets++;
+    c->frame_counter = 0;
+    c->n_poses = 0;
+    int r = push_pose(c, IDENTITY);
+    if (r) return r;
+    r = launch_reset_scene(c);
+    if (r) return r;
+    return launch_pose_set(c, IDENTITY, false);
+}
+
+inline void stamp(tfb_ctx* c, int i) {
+    if (c->timing) cudaEventRecord(c->ev[i], c->stream);
+}
+
+// cuda::computeDists + depthBilateralFilter + depthTruncation + depthBuildPyramid + computePointNormals (topfu.cpp:166-197)
+int do_preprocess(tfb_ctx* c, const uint16_t* depth_dev, bool maps_into_model) {
+    const tfb_params& p = c->p;
+    int r = launch_bilateral(c, depth_dev, c->lv[0].depth, p.cols, p.rows, p.bilateral_kernel_size, p.bilateral_sigma_spatial,
+                             p.bilateral_sigma_depth, p.icp_truncate_depth_dist, c->dists);
+    if (r) return r;
+    for (int i = 1; i < c->levels; ++i) {
+        r = launch_depth_pyr(c, c->lv[i - 1].depth, c->lv[i].depth, c->lv[i - 1].w, c->lv[i - 1].h, p.bilateral_sigma_depth);
+        if (r) return r;
+    }
+    for (int i = 0; i < c->levels; ++i) {
+        int div = 1 << i;  // Intr::operator()(level), src/precomp.cpp:10-14
+        // frame 0 ends with curr_.points_pyr.swap(prev_.points_pyr) (topfu.cpp:205-207): write the model maps directly
+        float4* v = maps_into_model ? c->lv[i].vprev : c->lv[i].vcurr;
+        float4* n = maps_into_model ? c->lv[i].nprev : c->lv[i].ncurr;
+        r = launch_points_normals(c, c->lv[i].depth, v, n, c->lv[i].w, c->lv[i].h, p.fx / div, p.fy / div, p.cx / div, p.cy / div);
+        if (r) return r;
+    }
+    return TFB_OK;
+}
+
+// ProjectiveICP::estimateTransform, projective_icp.cpp:169-212 — every iteration is one launch, nothing returns to the host
+int do_icp(tfb_ctx* c) {
+    const tfb_params& p = c->p;
+    int r = launch_icp_begin(c);
+    if (r) return r;
+    for (int l = c->levels - 1; l >= 0; --l) {
+        int div = 1 << l;  // setLevelIntr, projective_icp.cpp:17-23
+        for (int it = 0; it < p.icp_iters[l]; ++it) {
+            r = launch_icp_iteration(c, l, c->lv[l].vcurr, c->lv[l].ncurr, c->lv[l].vprev, c->lv[l].nprev, c->lv[l].w, c->lv[l].h,
+                                     p.fx / div, p.fy / div, p.cx / div, p.cy / div, true, nullptr);
+            if (r) return r;
+        }
+    }
+    return TFB_OK;
+}
+
+int do_frame(tfb_ctx* c, const uint16_t* depth_dev, int* ok) {
+    int r;
+    stamp(c, ST_PRE);
+    const bool first = (c->frame_counter == 0);
+    if ((r = do_preprocess(c, depth_dev, first))) return r;
+    if (first) {
+        stamp(c, ST_ICP);
+        stamp(c, ST_ALLOC);
+        if ((r = launch_allocate(c, c->dists))) return r;
+        stamp(c, ST_INTEG);
+        if ((r = launch_integrate(c, c->dists))) return r;
+        stamp(c, ST_EXPECT); stamp(c, ST_RAYCAST); stamp(c, ST_PYR);
+    } else {
+        stamp(c, ST_ICP);
+        if ((r = do_icp(c))) return r;
+        if ((r = launch_pose_update(c))) return r;
+        stamp(c, ST_ALLOC);
+        if ((r = launch_allocate(c, c->dists))) return r;
+        stamp(c, ST_INTEG);
+        if ((r = launch_integrate(c, c->dists))) return r;
+        stamp(c, ST_EXPECT);
+        if ((r = launch_expected_depths(c))) return r;
+        stamp(c, ST_RAYCAST);
+        if ((r = launch_icp_maps(c, c->lv[0].vprev, c->lv[0].nprev))) return r;
+        stamp(c, ST_PYR);
+        for (int i = 1; i < c->levels; ++i)
+            if ((r = launch_resize_points_normals(c, c->lv[i - 1].vprev, c->lv[i - 1].nprev, c->lv[i].vprev, c->lv[i].nprev,
+                                                  c->lv[i - 1].w, c->lv[i - 1].h)))
+                return r;
+    }
+    stamp(c, ST_FRAME);
+    if ((r = fetch_state(c))) return r;  // the one wait of the frame
+    if (c->timing) {
+        float t;
+        for (int i = ST_PRE; i < ST_FRAME; ++i) {
+            cudaEventElapsedTime(&t, c->ev[i], c->ev[i + 1]);
+            c->stage_ms[i] = t;
+        }
+        cudaEventElapsedTime(&t, c->ev[ST_UPLOAD], c->ev[ST_PRE]);
+        c->stage_ms[ST_UPLOAD] = t;
+        cudaEventElapsedTime(&t, c->ev[ST_UPLOAD], c->ev[ST_FRAME]);
+        c->stage_ms[ST_FRAME] = t;
+    }
+    c->voxel_updates_last = (long long)c->hs->voxel_updates;
+    if (first) {
+        c->frame_counter++;
+        *ok = 1;
+        return TFB_OK;
+    }
+    if (c->hs->icp_failed) {  // topfu.cpp:263-264: return reset(), false
+        c->voxel_updates_last = 0;
+        if ((r = do_reset(c))) return r;
+        *ok = 0;
+        return TFB_OK;
+    }
+    if ((r = push_pose(c, c->hs->pose_c2w))) return r;
+    c->frame_counter++;
+    *ok = 1;
+    return TFB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* tfb_version(void) { return "tfusion_b200 0.1 (sm_100a)"; }
+
+int tfb_default_params(tfb_params* p) {
+    if (!p) return TFB_ERR_ARG;
+    memset(p, 0, sizeof(*p));
+    p->cols = 640; p->rows = 480;
+    p->fx = 504.261f; p->fy = 503.905f; p->cx = 352.457f; p->cy = 272.202f;   // topfu.cpp:24
+    p->bilateral_sigma_depth = 0.04f; p->bilateral_sigma_spatial = 4.5f; p->bilateral_kernel_size = 7;
+    p->icp_truncate_depth_dist = 2.0f; p->icp_dist_thres = 0.1f; p->icp_angle_thres = 30.f * 0.017453293f;
+    p->icp_iters[0] = 10; p->icp_iters[1] = 5; p->icp_iters[2] = 4; p->icp_iters[3] = 0;
+    p->mu = 0.02f; p->max_w = 100; p->voxel_size = 0.005f; p->view_frustum_min = 0.2f; p->view_frustum_max = 3.0f;  // topfu.cpp:50
+    p->stop_integrating_at_max_w = 0;
+    p->num_blocks = 0x10000; p->num_buckets = 0x100000; p->excess_size = 0x20000;  // VoxelBlockHash.hpp:14-18
+    p->depth_cutoff_mm = 2047;
+    p->corrected_mode = 0; p->shard_rank = 0; p->shard_count = 1;
+    return TFB_OK;
+}
+
+int tfb_create(const tfb_params* p, void* stream, tfb_ctx** out) {
+    if (!p || !out) return TFB_ERR_ARG;
+    *out = nullptr;
+    if (p->cols <= 0 || p->rows <= 0 || (p->cols % 8) || (p->rows % 8)) return TFB_ERR_ARG;
+    if (p->num_buckets <= 0 || (p->num_buckets & (p->num_buckets - 1))) return TFB_ERR_ARG;
+    if (p->num_blocks <= 0 || p->excess_size <= 0 || p->voxel_size <= 0 || p->mu <= 0) return TFB_ERR_ARG;
+    if (p->shard_count < 1 || p->shard_rank < 0 || p->shard_rank >= p->shard_count) return TFB_ERR_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return TFB_ERR_CUDA;  // no CPU fallback, by design
+
+    tfb_ctx* c = new (std::nothrow) tfb_ctx();
+    if (!c) return TFB_ERR_NOMEM;
+    memset(c, 0, sizeof(*c));
+    c->p = *p;
+    cudaGetDevice(&c->device);
+    c->total_entries = p->num_buckets + p->excess_size;
+    c->hash_mask = p->num_buckets - 1;
+    c->levels = used_levels(*p);
+
+    cudaError_t e = cudaSuccess;
+    auto ok = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+    if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
+    else { ok(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+
+    const size_t npx = (size_t)p->cols * p->rows;
+    ok(dmalloc(&c->table, (size_t)c->total_entries));
+    ok(dmalloc(&c->vba, (size_t)p->num_blocks * BLOCK3));
+    ok(dmalloc(&c->vba_free, (size_t)p->num_blocks));
+    ok(dmalloc(&c->excess_free, (size_t)p->excess_size));
+    ok(dmalloc(&c->claim_key, (size_t)c->total_entries));
+    ok(dmalloc(&c->claimed, (size_t)c->total_entries));
+    ok(dmalloc(&c->vis_type, (size_t)c->total_entries));
+    ok(dmalloc(&c->vis_list[0], (size_t)c->total_entries));
+    ok(dmalloc(&c->vis_list[1], (size_t)c->total_entries));
+    ok(dmalloc(&c->minmax, npx / (MINMAX_SUB * MINMAX_SUB)));
+    ok(dmalloc(&c->raycast, npx));
+    ok(dmalloc(&c->dists, npx));
+    ok(dmalloc(&c->depth_in, npx));
+    {
+        int w = p->cols, h = p->rows;
+        for (int l = 0; l < MAX_LEVELS; ++l) {
+            c->lv[l].w = w; c->lv[l].h = h;
+            size_t n = (size_t)w * h;
+            ok(dmalloc(&c->lv[l].depth, n));
+            ok(dmalloc(&c->lv[l].vcurr, n)); ok(dmalloc(&c->lv[l].ncurr, n));
+            ok(dmalloc(&c->lv[l].vprev, n)); ok(dmalloc(&c->lv[l].nprev, n));
+            if (e == cudaSuccess) {
+                cudaMemsetAsync(c->lv[l].depth, 0, n * 2, c->stream);
+                cudaMemsetAsync(c->lv[l].vcurr, 0, n * 16, c->stream); cudaMemsetAsync(c->lv[l].ncurr, 0, n * 16, c->stream);
+                cudaMemsetAsync(c->lv[l].vprev, 0, n * 16, c->stream); cudaMemsetAsync(c->lv[l].nprev, 0, n * 16, c->stream);
+            }
+            w /= 2; h /= 2;
+        }
+    }
+    c->icp_max_blocks = div_up(p->cols, 32) * div_up(p->rows, 8);
+    ok(dmalloc(&c->icp_partial, (size_t)(ICP_TERMS + 1) * c->icp_max_blocks + 32));
+    ok(cudaMalloc((void**)&c->ds, sizeof(DevState) + 64 * sizeof(float)));
+    ok(cudaMallocHost((void**)&c->hs, sizeof(DevState)));
+    ok(cudaMallocHost((void**)&c->h_pose_stage, 64 * sizeof(float)));
+    ok(cudaMallocHost((void**)&c->h_icp27, 32 * sizeof(float)));
+    for (int i = 0; i < 16; ++i) ok(cudaEventCreate(&c->ev[i]));
+    if (e != cudaSuccess) {
+        free_all(c);
+        delete c;
+        return e == cudaErrorMemoryAllocation ? TFB_ERR_NOMEM : TFB_ERR_CUDA;
+    }
+    // RenderState_VH arrays are never initialised by the reference; zero them here
+    cudaMemsetAsync(c->ds, 0, sizeof(DevState) + 64 * sizeof(float), c->stream);
+    cudaMemsetAsync(c->vis_type, 0, (size_t)c->total_entries * sizeof(int), c->stream);
+    cudaMemsetAsync(c->claim_key, 0, (size_t)c->total_entries * sizeof(unsigned), c->stream);
+    cudaMemsetAsync(c->raycast, 0, npx * sizeof(float4), c->stream);
+    cudaMemsetAsync(c->dists, 0, npx * sizeof(float), c->stream);
+    {   // RenderState ctor fills the range image with (vf_min, vf_max), include/tfusion/RenderState.hpp:67-73
+        size_t n = npx / (MINMAX_SUB * MINMAX_SUB);
+        float2* tmp = (float2*)malloc(n * sizeof(float2));
+        for (size_t i = 0; i < n; ++i) tmp[i] = make_float2(p->view_frustum_min, p->view_frustum_max);
+        cudaMemcpy(c->minmax, tmp, n * sizeof(float2), cudaMemcpyHostToDevice);
+        free(tmp);
+    }
+    int r = do_reset(c);
+    if (r == TFB_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) r = TFB_ERR_CUDA;
+    if (r != TFB_OK) { free_all(c); delete c; return r; }
+    c->resets = 0;
+    *out = c;
+    return TFB_OK;
+}
+
+int tfb_destroy(tfb_ctx* c) {
+    if (!c) return TFB_ERR_ARG;
+    cudaStreamSynchronize(c->stream);
+    free_all(c);
+    delete c;
+    return TFB_OK;
+}
+
+int tfb_reset(tfb_ctx* c) {
+    if (!c) return TFB_ERR_ARG;
+    int r = do_reset(c);
+    if (r) return r;
+    TFB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return TFB_OK;
+}
+
+const char* tfb_last_error(const tfb_ctx* c) { return c ? c->err : "null context"; }
+
+int tfb_dev_alloc(void** dptr, size_t bytes) { return (dptr && cudaMalloc(dptr, bytes ? bytes : 1) == cudaSuccess) ? TFB_OK : TFB_ERR_NOMEM; }
+int tfb_dev_free(void* dptr) { return cudaFree(dptr) == cudaSuccess ? TFB_OK : TFB_ERR_CUDA; }
+int tfb_host_alloc_pinned(void** hptr, size_t bytes) { return (hptr && cudaMallocHost(hptr, bytes ? bytes : 1) == cudaSuccess) ? TFB_OK : TFB_ERR_NOMEM; }
+int tfb_host_free_pinned(void* hptr) { return cudaFreeHost(hptr) == cudaSuccess ? TFB_OK : TFB_ERR_CUDA; }
+
+int tfb_h2d(tfb_ctx* c, void* dst, const void* src, size_t bytes) {
+    if (!c || !dst || !src) return TFB_ERR_ARG;
+    TFB_CUDA(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    return TFB_OK;
+}
+int tfb_d2h(tfb_ctx* c, void* dst, const void* src, size_t bytes) {
+    if (!c || !dst || !src) return TFB_ERR_ARG;
+    TFB_CUDA(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    TFB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return TFB_OK;
+}
+int tfb_sync(tfb_ctx* c) {
+    if (!c) return TFB_ERR_ARG;
+    TFB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return TFB_OK;
+}
+
+// ---- image stages ------------------------------------------------------------------------------
+int tfb_compute_dists(tfb_ctx* c, const uint16_t* depth, float* dists, int cols, int rows) {
+    if (!c || !depth || !dists || cols <= 0 || rows <= 0) return TFB_ERR_ARG;
+    return launch_compute_dists(c, depth, dists, cols, rows);
+}
+int tfb_bilateral_filter(tfb_ctx* c, const uint16_t* src, uint16_t* dst, int cols, int rows, int ksz, float ss, float sd) {
+    if (!c || !src || !dst || cols <= 0 || rows <= 0) return TFB_ERR_ARG;
+    return launch_bilateral(c, src, dst, cols, rows, ksz, ss, sd, 0.f, nullptr);
+}
+int tfb_truncate_depth(tfb_ctx* c, uint16_t* depth, int cols, int rows, float max_dist) {
+    if (!c || !depth || cols <= 0 || rows <= 0) return TFB_ERR_ARG;
+    return launch_truncate(c, depth, cols, rows, max_dist);
+}
+int tfb_depth_pyr(tfb_ctx* c, const uint16_t* src, uint16_t* dst, int sw, int sh, float sd) {
+    if (!c || !src || !dst || sw < 2 || sh < 2) return TFB_ERR_ARG;
+    return launch_depth_pyr(c, src, dst, sw, sh, sd);
+}
+int tfb_compute_point_normals(tfb_ctx* c, const uint16_t* depth, float* points, float* normals, int cols, int rows, float fx, float fy,
+                              float cx, float cy) {
+    if (!c || !depth || !points || !normals || cols <= 0 || rows <= 0) return TFB_ERR_ARG;
+    return launch_points_normals(c, depth, (float4*)points, (float4*)normals, cols, rows, fx, fy, cx, cy);
+}
+int tfb_resize_points_normals(tfb_ctx* c, const float* points, const float* normals, float* po, float* no, int sw, int sh) {
+    if (!c || !points || !normals || !po || !no || sw < 2 || sh < 2) return TFB_ERR_ARG;
+    return launch_resize_points_normals(c, (const float4*)points, (const float4*)normals, (float4*)po, (float4*)no, sw, sh);
+}
+int tfb_preprocess(tfb_ctx* c, const uint16_t* depth_dev) {
+    if (!c || !depth_dev) return TFB_ERR_ARG;
+    return do_preprocess(c, depth_dev, false);
+}
+
+// ---- ICP -----------------------------------------------------------------------------------------
+int tfb_icp_reduce(tfb_ctx* c, int cols, int rows, float fx, float fy, float cx, float cy, const float aff[16], const float* vcurr,
+                   const float* ncurr, const float* vprev, const float* nprev, float out27_host[27]) {
+    if (!c || !aff || !vcurr || !ncurr || !vprev || !nprev || !out27_host) return TFB_ERR_ARG;
+    int r = launch_icp_begin(c);
+    if (r) return r;
+    TFB_CUDA(c, cudaStreamSynchronize(c->stream));
+    memcpy(c->h_pose_stage, aff, 64);
+    TFB_CUDA(c, cudaMemcpyAsync(c->ds->affine, c->h_pose_stage, 64, cudaMemcpyHostToDevice, c->stream));
+    float* d27 = reinterpret_cast<float*>(c->ds + 1) + 16;
+    r = launch_icp_iteration(c, 0, (const float4*)vcurr, (const float4*)ncurr, (const float4*)vprev, (const float4*)nprev, cols, rows, fx,
+                             fy, cx, cy, false, d27);
+    if (r) return r;
+    TFB_CUDA(c, cudaMemcpyAsync(c->h_icp27, d27, 27 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    TFB_CUDA(c, cudaStreamSynchronize(c->stream));
+    memcpy(out27_host, c->h_icp27, 27 * sizeof(float));
+    return TFB_OK;
+}
+
+int tfb_icp_estimate(tfb_ctx* c, float affine_out[16], int* ok) {
+    if (!c || !affine_out || !ok) return TFB_ERR_ARG;
+    int r = do_icp(c);
+    if (r) return r;
+    if ((r = fetch_state(c))) return r;
+    memcpy(affine_out, c->hs->affine, 64);
+    *ok = c->hs->icp_failed ? 0 : 1;
+    return TFB_OK;
+}
+
+// ---- scene / visualisation stages with an injected pose ------------------------------------------------
+int tfb_allocate_scene_from_depth(tfb_ctx* c, const float pose_w2c[16], const float* dists_dev) {
+    if (!c || !pose_w2c || !dists_dev) return TFB_ERR_ARG;
+    int r = launch_pose_set(c, pose_w2c, true);
+    if (r) return r;
+    return launch_allocate(c, dists_dev);
+}
+int tfb_integrate_into_scene(tfb_ctx* c, const float pose_w2c[16], const float* dists_dev) {
+    if (!c || !pose_w2c || !dists_dev) return TFB_ERR_ARG;
+    int r = launch_pose_set(c, pose_w2c, true);
+    if (r) return r;
+    r = launch_integrate(c, dists_dev);
+    if (r) return r;
+    if ((r = fetch_state(c))) return r;
+    c->voxel_updates_last = (long long)c->hs->voxel_updates;
+    return TFB_OK;
+}
+int tfb_create_expected_depths(tfb_ctx* c, const float pose_w2c[16]) {
+    if (!c || !pose_w2c) return TFB_ERR_ARG;
+    int r = launch_pose_set(c, pose_w2c, true);
+    if (r) return r;
+    return launch_expected_depths(c);
+}
+int tfb_create_icp_maps(tfb_ctx* c, const float pose_c2w[16], float* points_dev, float* normals_dev) {
+    if (!c || !pose_c2w || !points_dev || !normals_dev) return TFB_ERR_ARG;
+    int r = launch_pose_set(c, pose_c2w, false);
+    if (r) return r;
+    return launch_icp_maps(c, (float4*)points_dev, (float4*)normals_dev);
+}
+
+// ---- the frame ----------------------------------------------------------------------------------------
+int tfb_process_frame(tfb_ctx* c, const uint16_t* depth_host, size_t step_bytes, int* ok) {
+    if (!c || !depth_host || !ok) return TFB_ERR_ARG;
+    const size_t row = (size_t)c->p.cols * sizeof(uint16_t);
+    if (step_bytes == 0) step_bytes = row;
+    if (step_bytes < row) return TFB_ERR_ARG;
+    stamp(c, ST_UPLOAD);
+    TFB_CUDA(c, cudaMemcpy2DAsync(c->depth_in, row, depth_host, step_bytes, row, c->p.rows, cudaMemcpyHostToDevice, c->stream));
+    return do_frame(c, c->depth_in, ok);
+}
+
+int tfb_process_frame_device(tfb_ctx* c, const uint16_t* depth_dev, int* ok) {
+    if (!c || !depth_dev || !ok) return TFB_ERR_ARG;
+    stamp(c, ST_UPLOAD);
+    return do_frame(c, depth_dev, ok);
+}
+
+int tfb_get_pose(const tfb_ctx* c, int time, float out16[16]) {
+    if (!c || !out16 || c->n_poses == 0) return TFB_ERR_ARG;
+    if (time > c->n_poses || time < 0) time = c->n_poses - 1;   // topfu.cpp:156-157
+    if (time >= c->n_poses) time = c->n_poses - 1;
+    memcpy(out16, c->poses + (size_t)time * 16, 64);
+    return TFB_OK;
+}
+int tfb_num_poses(const tfb_ctx* c) { return c ? c->n_poses : 0; }
+
+// ---- inspection -----------------------------------------------------------------------------------------
+int tfb_get_counters(tfb_ctx* c, long long out[8]) {
+    if (!c || !out) return TFB_ERR_ARG;
+    int r = fetch_state(c);
+    if (r) return r;
+    out[0] = c->hs->n_visible; out[1] = c->hs->last_free_block; out[2] = c->hs->last_free_excess; out[3] = c->hs->n_new_frame;
+    out[4] = c->frame_counter; out[5] = c->resets; out[6] = c->hs->n_next;
+    out[7] = (long long)c->p.num_blocks - 1 - c->hs->last_free_block;
+    return TFB_OK;
+}
+long long tfb_voxel_updates_last(tfb_ctx* c) { return c ? c->voxel_updates_last : 0; }
+int tfb_total_entries(const tfb_ctx* c) { return c ? c->total_entries : 0; }
+
+int tfb_export_table(tfb_ctx* c, void* host) {
+    if (!c || !host) return TFB_ERR_ARG;
+    return tfb_d2h(c, host, c->table, (size_t)c->total_entries * sizeof(HashEntry));
+}
+int tfb_export_vis_type(tfb_ctx* c, uint8_t* host) {
+    if (!c || !host) return TFB_ERR_ARG;
+    int* tmp = (int*)malloc((size_t)c->total_entries * sizeof(int));
+    if (!tmp) return TFB_ERR_NOMEM;
+    int r = tfb_d2h(c, tmp, c->vis_type, (size_t)c->total_entries * sizeof(int));
+    if (r == TFB_OK)
+        for (int i = 0; i < c->total_entries; ++i) host[i] = (uint8_t)tmp[i];
+    free(tmp);
+    return r;
+}
+int tfb_export_visible_ids(tfb_ctx* c, int32_t* host, int capacity, int* n) {
+    if (!c || !host || !n) return TFB_ERR_ARG;
+    int r = fetch_state(c);
+    if (r) return r;
+    *n = c->hs->n_visible;
+    if (*n > capacity) return TFB_ERR_ARG;
+    if (*n == 0) return TFB_OK;
+    return tfb_d2h(c, host, c->vis_list[c->hs->cur_list & 1], (size_t)*n * sizeof(int));
+}
+int tfb_export_block(tfb_ctx* c, int ptr, void* host) {
+    if (!c || !host || ptr < 0 || ptr >= c->p.num_blocks) return TFB_ERR_ARG;
+    return tfb_d2h(c, host, c->vba + (size_t)ptr * BLOCK3, BLOCK3 * sizeof(Voxel));
+}
+int tfb_export_minmax(tfb_ctx* c, float* host) {
+    if (!c || !host) return TFB_ERR_ARG;
+    return tfb_d2h(c, host, c->minmax, (size_t)c->p.cols * c->p.rows / (MINMAX_SUB * MINMAX_SUB) * sizeof(float2));
+}
+int tfb_export_raycast(tfb_ctx* c, float* host) {
+    if (!c || !host) return TFB_ERR_ARG;
+    return tfb_d2h(c, host, c->raycast, (size_t)c->p.cols * c->p.rows * sizeof(float4));
+}
+int tfb_export_dists(tfb_ctx* c, float* host) {
+    if (!c || !host) return TFB_ERR_ARG;
+    return tfb_d2h(c, host, c->dists, (size_t)c->p.cols * c->p.rows * sizeof(float));
+}
+
+void* tfb_level_ptr(tfb_ctx* c, int which, int level) {
+    if (!c || level < 0 || level >= MAX_LEVELS) return nullptr;
+    switch (which) {
+        case 0: return c->lv[level].depth;
+        case 1: return c->lv[level].vcurr;
+        case 2: return c->lv[level].ncurr;
+        case 3: return c->lv[level].vprev;
+        case 4: return c->lv[level].nprev;
+        case 5: return c->dists;
+    }
+    return nullptr;
+}
+static size_t level_bytes(tfb_ctx* c, int which, int level) {
+    size_t n = (size_t)c->lv[level].w * c->lv[level].h;
+    if (which == 0) return n * 2;
+    if (which == 5) return (size_t)c->p.cols * c->p.rows * 4;
+    return n * 16;
+}
+int tfb_export_level(tfb_ctx* c, int which, int level, void* host) {
+    void* p = tfb_level_ptr(c, which, level);
+    if (!p || !host) return TFB_ERR_ARG;
+    return tfb_d2h(c, host, p, level_bytes(c, which, level));
+}
+int tfb_import_level(tfb_ctx* c, int which, int level, const void* host) {
+    void* p = tfb_level_ptr(c, which, level);
+    if (!p || !host) return TFB_ERR_ARG;
+    TFB_CUDA(c, cudaMemcpyAsync(p, host, level_bytes(c, which, level), cudaMemcpyHostToDevice, c->stream));
+    TFB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return TFB_OK;
+}
+
+// ---- timing -------------------------------------------------------------------------------------------
+int tfb_timing_enable(tfb_ctx* c, int on) {
+    if (!c) return TFB_ERR_ARG;
+    c->timing = on != 0;
+    return TFB_OK;
+}
+int tfb_timing_last_ms(tfb_ctx* c, float out9[9]) {
+    if (!c || !out9) return TFB_ERR_ARG;
+    memcpy(out9, c->stage_ms, sizeof(float) * 9);
+    return TFB_OK;
+}
+long long tfb_kernel_launches(const tfb_ctx* c) { return c ? c->launches : 0; }
+
+}  // extern "C"

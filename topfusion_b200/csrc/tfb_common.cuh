@@ -1,0 +1,179 @@
+// tfusion_b200 internals shared by the translation units.  sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/tfusion_b200.h"
+
+namespace tfb {
+
+constexpr int BLOCK = 8;          // SDF_BLOCK_SIZE, include/tfusion/cuda/VoxelBlockHash.hpp:10
+constexpr int BLOCK3 = 512;       // SDF_BLOCK_SIZE3
+constexpr int MINMAX_SUB = 8;     // minmaximg_subsample, VisualisationEngine_Shared.hpp:7
+constexpr int MAX_LEVELS = 4;     // ProjectiveICP::MAX_PYRAMID_LEVELS
+constexpr int ICP_TERMS = 27;     // proj_icp.cu:13-28
+constexpr int NUM_SMS = 148;      // B200
+#define TFB_FAR_AWAY 999999.9f    // VisualisationEngine_Shared.hpp:17-23
+#define TFB_VERY_CLOSE 0.05f
+
+// 16-byte hash entry (VoxelBlockHash.hpp:32-44), moved as one 128-bit word
+struct __align__(16) HashEntry {
+    short pos[3];
+    short pad_;
+    int offset;
+    int ptr;
+};
+static_assert(sizeof(HashEntry) == 16, "HashEntry");
+
+// Voxel_s (VoxelTypes.hpp:69-92): {short sdf; uchar w_depth; pad}
+struct __align__(4) Voxel {
+    short sdf;
+    unsigned char w_depth;
+    unsigned char pad_;
+};
+static_assert(sizeof(Voxel) == 4, "Voxel");
+
+// Everything a frame needs that is decided on the device lives here, so no stage has to wait
+// for the host (the reference syncs 22 times per frame).
+struct DevState {
+    // poses, all float
+    float pose_c2w[16];    // row-major, TopFu::poses_.back()
+    float pose_w2c[16];    // row-major, pose.inv()
+    float M_w2c[16];       // column-major Matrix4f of pose_w2c ("M_d")
+    float invM_w2c[16];    // column-major cofactor inverse of M_w2c (SceneReconstructionEngine_host.cu:103-104)
+    float M_c2w[16];       // column-major of pose_c2w (raycast "invM")
+    float affine[16];      // ICP running estimate, row-major
+    // free lists (LocalVBA.lastFreeBlockId, VoxelBlockHash.lastFreeExcessListId)
+    int last_free_block;
+    int last_free_excess;
+    // visible list bookkeeping
+    int n_visible;         // entries in the current list
+    int n_next;            // entries accumulated in the next list (raycast extras, new marks, survivors)
+    int n_claimed;         // slots claimed for allocation this frame
+    int n_new_frame;       // blocks allocated this frame
+    int n_extras;          // raycast-marked entries carried into the next frame
+    int cur_list;          // which of the two list buffers is current (flipped on the device, never by the host)
+    // ICP
+    int icp_failed;        // sticky for the frame: |det| < 1e-15 or NaN (projective_icp.cpp:197-203)
+    unsigned int icp_ticket;
+    int icp_corresp;
+    // statistics
+    unsigned long long voxel_updates;
+    int pad_[2];
+};
+
+struct LevelBuf {
+    int w, h;
+    uint16_t* depth;   // current filtered depth
+    float4* vcurr;
+    float4* ncurr;
+    float4* vprev;     // model maps
+    float4* nprev;
+};
+
+}  // namespace tfb
+
+struct tfb_ctx {
+    tfb_params p;
+    cudaStream_t stream;
+    bool own_stream;
+    int device;
+    char err[256];
+
+    int total_entries;
+    int hash_mask;
+    int levels;
+
+    // scene
+    tfb::HashEntry* table;
+    tfb::Voxel* vba;
+    int* vba_free;
+    int* excess_free;
+    // allocation scratch
+    unsigned int* claim_key;   // per slot, 0 = unclaimed
+    int* claimed;              // compact list of claimed slots
+    // render state
+    int* vis_type;             // per slot (reference: uchar entriesVisibleType)
+    int* vis_list[2];          // double-buffered visibleEntryIDs; DevState::cur_list says which is current
+    float2* minmax;            // (rows/8) x (cols/8)
+    float4* raycast;           // rows x cols
+    // frames
+    tfb::LevelBuf lv[tfb::MAX_LEVELS];
+    float* dists;
+    uint16_t* depth_in;        // device copy of the raw frame
+    // ICP
+    float* icp_partial;        // [ICP_TERMS][max_blocks]
+    int icp_max_blocks;
+    // state
+    tfb::DevState* ds;         // device
+    tfb::DevState* hs;         // pinned host mirror
+    float* h_pose_stage;       // pinned, 64 floats
+    float* h_icp27;            // pinned
+
+    // host bookkeeping
+    int frame_counter;
+    int resets;
+    float* poses;              // host history, 16 floats each
+    int n_poses, cap_poses;
+    long long launches;
+    long long voxel_updates_last;
+
+    // timing
+    bool timing;
+    cudaEvent_t ev[16];
+    float stage_ms[9];
+};
+
+namespace tfb {
+
+inline int set_err(tfb_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess) {
+    if (c) {
+        if (e != cudaSuccess) snprintf(c->err, sizeof(c->err), "%s: %s", what, cudaGetErrorString(e));
+        else snprintf(c->err, sizeof(c->err), "%s", what);
+    }
+    return code;
+}
+
+#define TFB_CUDA(c, call)                                                         \
+    do {                                                                          \
+        cudaError_t e__ = (call);                                                 \
+        if (e__ != cudaSuccess) return tfb::set_err((c), TFB_ERR_CUDA, #call, e__); \
+    } while (0)
+
+#define TFB_LAUNCH_CHECK(c)                                                              \
+    do {                                                                                 \
+        (c)->launches++;                                                                 \
+        cudaError_t e__ = cudaGetLastError();                                            \
+        if (e__ != cudaSuccess) return tfb::set_err((c), TFB_ERR_CUDA, "kernel launch", e__); \
+    } while (0)
+
+inline int div_up(int a, int b) { return (a + b - 1) / b; }
+
+// stage launchers implemented in the .cu files ------------------------------------------------
+// imgproc
+int launch_compute_dists(tfb_ctx* c, const uint16_t* depth, float* dists, int w, int h);
+int launch_bilateral(tfb_ctx* c, const uint16_t* src, uint16_t* dst, int w, int h, int ksz, float ss, float sd_m,
+                     float trunc_m, float* dists_or_null);
+int launch_truncate(tfb_ctx* c, uint16_t* depth, int w, int h, float max_dist);
+int launch_depth_pyr(tfb_ctx* c, const uint16_t* src, uint16_t* dst, int sw, int sh, float sigma_depth_m);
+int launch_points_normals(tfb_ctx* c, const uint16_t* depth, float4* pts, float4* nrm, int w, int h, float fx, float fy,
+                          float cx, float cy);
+int launch_resize_points_normals(tfb_ctx* c, const float4* v, const float4* n, float4* vo, float4* no, int sw, int sh);
+// icp
+int launch_icp_iteration(tfb_ctx* c, int level, const float4* vcurr, const float4* ncurr, const float4* vprev,
+                         const float4* nprev, int w, int h, float fx, float fy, float cx, float cy, bool solve,
+                         float* out27_dev);
+int launch_icp_begin(tfb_ctx* c);
+int launch_pose_update(tfb_ctx* c);         // poses.back() * affine and all derived matrices
+int launch_pose_set(tfb_ctx* c, const float* pose_row_major_host, bool is_w2c);
+// scene
+int launch_reset_scene(tfb_ctx* c);
+int launch_allocate(tfb_ctx* c, const float* dists);
+int launch_integrate(tfb_ctx* c, const float* dists);
+// vis
+int launch_expected_depths(tfb_ctx* c);
+int launch_icp_maps(tfb_ctx* c, float4* points, float4* normals);
+
+}  // namespace tfb

@@ -116,8 +116,11 @@ def intrinsics_for(cols: int, rows: int):
 
 def render_depth(scene: Scene, pose_c2w: np.ndarray, cols: int = 640, rows: int = 480,
                  intr=None, noise_mm: float = 0.0, seed: int = 1234,
-                 max_mm: int = 65535) -> np.ndarray:
-    """z-depth in mm (u16), 0 = miss.  Ray parameter t equals camera z because dir_cam.z = 1."""
+                 max_mm: int = 10000) -> np.ndarray:
+    """z-depth in mm (u16), 0 = miss.  Ray parameter t equals camera z because dir_cam.z = 1.
+
+    Returns beyond max_mm (10 m, a depth sensor's range) are dropped: the reference's bilateral kernel squares
+    (value - depth) in int32 (imgproc.cu:36), which overflows for differences above 46 340 mm."""
     fx, fy, cx, cy = intr if intr is not None else intrinsics_for(cols, rows)
     u = (np.arange(cols, dtype=np.float64) - cx) / fx
     v = (np.arange(rows, dtype=np.float64) - cy) / fy
