@@ -164,6 +164,20 @@ TFB_API int tfb_timing_enable(tfb_ctx* c, int on);
 TFB_API int tfb_timing_last_ms(tfb_ctx* c, float out9[9]);
 /* number of kernels this library launched since the context was created */
 TFB_API long long tfb_kernel_launches(const tfb_ctx* c);
+/* overwrite a 256 MB scratch buffer on the context stream: evicts the 126 MB L2 between timed steps */
+TFB_API int tfb_flush_l2(tfb_ctx* c);
+/* cuda::setDevice, src/core.cpp — must precede tfb_create in a multi-GPU process (one rank per GPU) */
+TFB_API int tfb_set_device(int device);
+/* event markers on the context stream: tfb_mark(c, a) ... tfb_mark(c, b); tfb_elapsed_ms(c, a, b, &ms) */
+TFB_API int tfb_mark(tfb_ctx* c, int slot);
+TFB_API int tfb_elapsed_ms(tfb_ctx* c, int slot_a, int slot_b, float* ms);
+/* per-launch timing: when enabled every kernel launch is bracketed by two events on the context stream and the
+ * durations are accumulated per kernel (adds ~2 us per launch; keep it off in throughput runs) */
+TFB_API int tfb_ktiming_enable(tfb_ctx* c, int on);
+TFB_API int tfb_ktiming_reset(tfb_ctx* c);
+TFB_API int tfb_ktiming_count(void);
+TFB_API const char* tfb_ktiming_name(int id);
+TFB_API int tfb_ktiming_get(tfb_ctx* c, int id, double* total_ms, long long* launches);
 
 #ifdef __cplusplus
 }

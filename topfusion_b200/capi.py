@@ -66,6 +66,7 @@ def lib() -> C.CDLL:
         L.tfb_voxel_updates_last.restype = C.c_longlong
         L.tfb_kernel_launches.restype = C.c_longlong
         L.tfb_level_ptr.restype = C.c_void_p
+        L.tfb_ktiming_name.restype = C.c_char_p
         for name, args in {
             "tfb_create": [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)],
             "tfb_dev_alloc": [C.POINTER(C.c_void_p), C.c_size_t],
@@ -387,6 +388,32 @@ class Context:
 
     def level_ptr(self, which: int, level: int) -> int:
         return int(self.L.tfb_level_ptr(self.h, C.c_int(which), C.c_int(level)))
+
+    def mark(self, slot: int):
+        self._ck(self.L.tfb_mark(self.h, C.c_int(slot)))
+
+    def elapsed_ms(self, a: int, b: int) -> float:
+        ms = C.c_float(0)
+        self._ck(self.L.tfb_elapsed_ms(self.h, C.c_int(a), C.c_int(b), C.byref(ms)))
+        return float(ms.value)
+
+    def flush_l2(self):
+        self._ck(self.L.tfb_flush_l2(self.h))
+
+    def ktiming(self, on: bool = True, reset: bool = True):
+        self._ck(self.L.tfb_ktiming_enable(self.h, C.c_int(1 if on else 0)))
+        if reset:
+            self._ck(self.L.tfb_ktiming_reset(self.h))
+
+    def kernel_times(self) -> dict:
+        """{kernel name: (total_ms, launches)} accumulated while ktiming was on"""
+        out = {}
+        for i in range(int(self.L.tfb_ktiming_count())):
+            ms, n = C.c_double(0), C.c_longlong(0)
+            self._ck(self.L.tfb_ktiming_get(self.h, C.c_int(i), C.byref(ms), C.byref(n)))
+            if n.value:
+                out[self.L.tfb_ktiming_name(C.c_int(i)).decode()] = (float(ms.value), int(n.value))
+        return out
 
     def timing(self, on: bool = True):
         self._ck(self.L.tfb_timing_enable(self.h, C.c_int(1 if on else 0)))

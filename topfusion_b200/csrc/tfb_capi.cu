@@ -32,7 +32,7 @@ void free_all(tfb_ctx* c) {
     cudaFree(c->table); cudaFree(c->vba); cudaFree(c->vba_free); cudaFree(c->excess_free);
     cudaFree(c->claim_key); cudaFree(c->claimed); cudaFree(c->vis_type); cudaFree(c->vis_list[0]); cudaFree(c->vis_list[1]);
     cudaFree(c->minmax); cudaFree(c->raycast); cudaFree(c->dists); cudaFree(c->depth_in); cudaFree(c->icp_partial);
-    cudaFree(c->ds);
+    cudaFree(c->ds); cudaFree(c->l2_scratch);
     for (int l = 0; l < MAX_LEVELS; ++l) {
         cudaFree(c->lv[l].depth); cudaFree(c->lv[l].vcurr); cudaFree(c->lv[l].ncurr); cudaFree(c->lv[l].vprev); cudaFree(c->lv[l].nprev);
     }
@@ -41,6 +41,13 @@ void free_all(tfb_ctx* c) {
     if (c->h_icp27) cudaFreeHost(c->h_icp27);
     for (int i = 0; i < 16; ++i)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 8; ++i)
+        if (c->mark_ev[i]) cudaEventDestroy(c->mark_ev[i]);
+    if (c->kt_ev) {
+        for (int i = 0; i < KT_MAX_EVENTS; ++i)
+            if (c->kt_ev[i]) cudaEventDestroy(c->kt_ev[i]);
+        free(c->kt_ev);
+    }
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     free(c->poses);
 }
@@ -62,6 +69,17 @@ const float IDENTITY[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
 int fetch_state(tfb_ctx* c) {
     TFB_CUDA(c, cudaMemcpyAsync(c->hs, c->ds, sizeof(DevState), cudaMemcpyDeviceToHost, c->stream));
     TFB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->kt_n) {  // fold the per-launch event pairs recorded since the last sync
+        int n = c->kt_n & ~0x40000000;
+        for (int i = 0; i + 1 < n; i += 2) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, c->kt_ev[i], c->kt_ev[i + 1]) == cudaSuccess) {
+                c->kt_ms[c->kt_id[i / 2]] += t;
+                c->kt_cnt[c->kt_id[i / 2]]++;
+            }
+        }
+        c->kt_n = 0;
+    }
     return TFB_OK;
 }
 
@@ -263,6 +281,10 @@ int tfb_create(const tfb_params* p, void* stream, tfb_ctx** out) {
     ok(cudaMallocHost((void**)&c->h_pose_stage, 64 * sizeof(float)));
     ok(cudaMallocHost((void**)&c->h_icp27, 32 * sizeof(float)));
     for (int i = 0; i < 16; ++i) ok(cudaEventCreate(&c->ev[i]));
+    for (int i = 0; i < 8; ++i) ok(cudaEventCreate(&c->mark_ev[i]));
+    c->kt_ev = (cudaEvent_t*)calloc(KT_MAX_EVENTS, sizeof(cudaEvent_t));
+    if (!c->kt_ev) ok(cudaErrorMemoryAllocation);
+    else for (int i = 0; i < KT_MAX_EVENTS; ++i) ok(cudaEventCreate(&c->kt_ev[i]));
     if (e != cudaSuccess) {
         free_all(c);
         delete c;
@@ -541,5 +563,54 @@ int tfb_timing_last_ms(tfb_ctx* c, float out9[9]) {
     return TFB_OK;
 }
 long long tfb_kernel_launches(const tfb_ctx* c) { return c ? c->launches : 0; }
+
+// write a buffer larger than the 126 MB L2 so the next step starts from HBM (bench timing hygiene)
+int tfb_flush_l2(tfb_ctx* c) {
+    if (!c) return TFB_ERR_ARG;
+    const size_t bytes = (size_t)256 << 20;
+    if (!c->l2_scratch) TFB_CUDA(c, cudaMalloc(&c->l2_scratch, bytes));
+    c->l2_toggle ^= 1;
+    TFB_CUDA(c, cudaMemsetAsync(c->l2_scratch, c->l2_toggle, bytes, c->stream));
+    return TFB_OK;
+}
+
+int tfb_set_device(int device) { return cudaSetDevice(device) == cudaSuccess ? TFB_OK : TFB_ERR_CUDA; }
+
+int tfb_mark(tfb_ctx* c, int slot) {
+    if (!c || slot < 0 || slot >= 8) return TFB_ERR_ARG;
+    TFB_CUDA(c, cudaEventRecord(c->mark_ev[slot], c->stream));
+    return TFB_OK;
+}
+int tfb_elapsed_ms(tfb_ctx* c, int slot_a, int slot_b, float* ms) {
+    if (!c || !ms || slot_a < 0 || slot_a >= 8 || slot_b < 0 || slot_b >= 8) return TFB_ERR_ARG;
+    TFB_CUDA(c, cudaEventSynchronize(c->mark_ev[slot_b]));
+    TFB_CUDA(c, cudaEventElapsedTime(ms, c->mark_ev[slot_a], c->mark_ev[slot_b]));
+    return TFB_OK;
+}
+
+static const char* const KNAMES[K_COUNT] = {
+    "k_bilateral", "k_depth_pyr", "k_points_normals", "k_resize_points_normals", "k_compute_dists", "k_truncate",
+    "k_icp_begin", "k_icp_iteration[L0]", "k_icp_iteration[L1]", "k_icp_iteration[L2]", "k_icp_iteration[L3]", "k_pose_update",
+    "k_pose_set", "k_set_type3", "k_mark", "k_alloc", "k_visible_list", "k_list_flip", "k_integrate_begin", "k_integrate",
+    "k_minmax_init", "k_expected_depths", "k_raycast", "k_icp_maps", "k_reset_scene"};
+
+int tfb_ktiming_enable(tfb_ctx* c, int on) {
+    if (!c) return TFB_ERR_ARG;
+    c->ktiming = on != 0;
+    return TFB_OK;
+}
+int tfb_ktiming_reset(tfb_ctx* c) {
+    if (!c) return TFB_ERR_ARG;
+    for (int i = 0; i < K_COUNT; ++i) { c->kt_ms[i] = 0; c->kt_cnt[i] = 0; }
+    return TFB_OK;
+}
+int tfb_ktiming_count(void) { return K_COUNT; }
+const char* tfb_ktiming_name(int id) { return (id >= 0 && id < K_COUNT) ? KNAMES[id] : ""; }
+int tfb_ktiming_get(tfb_ctx* c, int id, double* total_ms, long long* launches) {
+    if (!c || id < 0 || id >= K_COUNT || !total_ms || !launches) return TFB_ERR_ARG;
+    *total_ms = c->kt_ms[id];
+    *launches = c->kt_cnt[id];
+    return TFB_OK;
+}
 
 }  // extern "C"

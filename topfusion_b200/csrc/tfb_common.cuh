@@ -9,6 +9,15 @@
 
 namespace tfb {
 
+// kernel ids for the per-launch CUDA-event timing (tfb_ktiming_*)
+enum KernelId {
+    K_BILATERAL = 0, K_DEPTH_PYR, K_POINTS_NORMALS, K_RESIZE_MAPS, K_COMPUTE_DISTS, K_TRUNCATE,
+    K_ICP_BEGIN, K_ICP_L0, K_ICP_L1, K_ICP_L2, K_ICP_L3, K_POSE_UPDATE, K_POSE_SET,
+    K_SET_TYPE3, K_MARK, K_ALLOC, K_VISIBLE_LIST, K_LIST_FLIP, K_INTEGRATE_BEGIN, K_INTEGRATE,
+    K_MINMAX_INIT, K_EXPECTED_DEPTHS, K_RAYCAST, K_ICP_MAPS, K_RESET_SCENE, K_COUNT
+};
+constexpr int KT_MAX_EVENTS = 512;
+
 constexpr int BLOCK = 8;          // SDF_BLOCK_SIZE, include/tfusion/cuda/VoxelBlockHash.hpp:10
 constexpr int BLOCK3 = 512;       // SDF_BLOCK_SIZE3
 constexpr int MINMAX_SUB = 8;     // minmaximg_subsample, VisualisationEngine_Shared.hpp:7
@@ -124,6 +133,16 @@ struct tfb_ctx {
     bool timing;
     cudaEvent_t ev[16];
     float stage_ms[9];
+    // per-launch timing (off by default): event pairs recorded around every launch, folded after the frame's sync
+    bool ktiming;
+    cudaEvent_t* kt_ev;          // KT_MAX_EVENTS
+    int kt_n;                    // events used this frame
+    unsigned char kt_id[tfb::KT_MAX_EVENTS / 2];
+    double kt_ms[tfb::K_COUNT];
+    long long kt_cnt[tfb::K_COUNT];
+    cudaEvent_t mark_ev[8];
+    void* l2_scratch;
+    int l2_toggle;
 };
 
 namespace tfb {
@@ -142,9 +161,24 @@ inline int set_err(tfb_ctx* c, int code, const char* what, cudaError_t e = cudaS
         if (e__ != cudaSuccess) return tfb::set_err((c), TFB_ERR_CUDA, #call, e__); \
     } while (0)
 
+// TFB_KT(c, id): put in front of a launch; TFB_LAUNCH_CHECK(c) behind it closes the pair
+#define TFB_KT(c, id)                                                                    \
+    do {                                                                                 \
+        if ((c)->ktiming && (c)->kt_n + 2 <= tfb::KT_MAX_EVENTS) {                       \
+            (c)->kt_id[(c)->kt_n / 2] = (unsigned char)(id);                             \
+            cudaEventRecord((c)->kt_ev[(c)->kt_n], (c)->stream);                         \
+            (c)->kt_n |= 0x40000000;                                                     \
+        }                                                                                \
+    } while (0)
+
 #define TFB_LAUNCH_CHECK(c)                                                              \
     do {                                                                                 \
         (c)->launches++;                                                                 \
+        if ((c)->kt_n & 0x40000000) {                                                    \
+            (c)->kt_n &= ~0x40000000;                                                    \
+            cudaEventRecord((c)->kt_ev[(c)->kt_n + 1], (c)->stream);                     \
+            (c)->kt_n += 2;                                                              \
+        }                                                                                \
         cudaError_t e__ = cudaGetLastError();                                            \
         if (e__ != cudaSuccess) return tfb::set_err((c), TFB_ERR_CUDA, "kernel launch", e__); \
     } while (0)

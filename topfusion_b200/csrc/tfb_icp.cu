@@ -303,6 +303,7 @@ __global__ void k_icp_begin(DevState* ds) {
 }
 
 int launch_icp_begin(tfb_ctx* c) {
+    TFB_KT(c, K_ICP_BEGIN);
     k_icp_begin<<<1, 32, 0, c->stream>>>(c->ds);
     TFB_LAUNCH_CHECK(c);
     return TFB_OK;
@@ -317,10 +318,10 @@ int launch_icp_iteration(tfb_ctx* c, int level, const float4* vcurr, const float
     a.dist2_thres = c->p.icp_dist_thres * c->p.icp_dist_thres;
     // enough CTAs to cover the SMs at the coarse levels, four rows per thread at full resolution
     a.rows_per_thread = ((long long)w * h >= 200000) ? 4 : 1;
-    (void)level;
     dim3 block(ICP_TX, ICP_TY), grid(div_up(w, ICP_TX), div_up(h, ICP_TY * a.rows_per_thread));
     a.nblk = grid.x * grid.y;
     if (a.nblk > c->icp_max_blocks) return set_err(c, TFB_ERR_ARG, "icp: image larger than the partial buffer");
+    TFB_KT(c, K_ICP_L0 + level);
     k_icp_iteration<<<grid, block, 0, c->stream>>>(a, c->ds, c->icp_partial, solve ? 1 : 0, out27_dev);
     TFB_LAUNCH_CHECK(c);
     return TFB_OK;

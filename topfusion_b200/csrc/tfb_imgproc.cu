@@ -26,6 +26,7 @@ __global__ void __launch_bounds__(256) k_compute_dists(const uint16_t* __restric
 
 int launch_compute_dists(tfb_ctx* c, const uint16_t* depth, float* dists, int w, int h) {
     int n = w * h;
+    TFB_KT(c, K_COMPUTE_DISTS);
     k_compute_dists<<<div_up(n, 256), 256, 0, c->stream>>>(depth, dists, n, c->p.depth_cutoff_mm);
     TFB_LAUNCH_CHECK(c);
     return TFB_OK;
@@ -88,6 +89,7 @@ int launch_bilateral(tfb_ctx* c, const uint16_t* src, uint16_t* dst, int w, int 
     int R = ksz / 2;
     size_t smem = (size_t)(BF_TX + 2 * R) * (BF_TY + 2 * R) * sizeof(uint16_t);
     dim3 block(BF_TX, BF_TY), grid(div_up(w, BF_TX), div_up(h, BF_TY));
+    TFB_KT(c, K_BILATERAL);
     k_bilateral<<<grid, block, smem, c->stream>>>(src, dst, dists_or_null, w, h, ksz, ss, sd, trunc_mm, c->p.depth_cutoff_mm);
     TFB_LAUNCH_CHECK(c);
     return TFB_OK;
@@ -100,6 +102,7 @@ __global__ void __launch_bounds__(256) k_truncate(uint16_t* depth, int n, int ma
 
 int launch_truncate(tfb_ctx* c, uint16_t* depth, int w, int h, float max_dist) {
     int n = w * h;
+    TFB_KT(c, K_TRUNCATE);
     k_truncate<<<div_up(n, 256), 256, 0, c->stream>>>(depth, n, (int)(unsigned short)(max_dist * 1000.f));
     TFB_LAUNCH_CHECK(c);
     return TFB_OK;
@@ -142,6 +145,7 @@ int launch_depth_pyr(tfb_ctx* c, const uint16_t* src, uint16_t* dst, int sw, int
     float thr = sigma_depth_m * 1000 * 3;  // imgproc.cu:132,138
     int dw = sw / 2, dh = sh / 2;
     dim3 block(PY_TX, PY_TY), grid(div_up(dw, PY_TX), div_up(dh, PY_TY));
+    TFB_KT(c, K_DEPTH_PYR);
     k_depth_pyr<<<grid, block, 0, c->stream>>>(src, dst, sw, sh, dw, dh, thr);
     TFB_LAUNCH_CHECK(c);
     return TFB_OK;
@@ -182,6 +186,7 @@ __global__ void __launch_bounds__(256) k_points_normals(const uint16_t* __restri
 int launch_points_normals(tfb_ctx* c, const uint16_t* depth, float4* pts, float4* nrm, int w, int h, float fx, float fy, float cx,
                           float cy) {
     dim3 block(32, 8), grid(div_up(w, 32), div_up(h, 8));
+    TFB_KT(c, K_POINTS_NORMALS);
     k_points_normals<<<grid, block, 0, c->stream>>>(depth, pts, nrm, w, h, 1.f / fx, 1.f / fy, cx, cy);
     TFB_LAUNCH_CHECK(c);
     return TFB_OK;
@@ -216,6 +221,7 @@ __global__ void __launch_bounds__(256) k_resize_points_normals(const float4* __r
 int launch_resize_points_normals(tfb_ctx* c, const float4* v, const float4* n, float4* vo, float4* no, int sw, int sh) {
     int dw = sw / 2, dh = sh / 2;
     dim3 block(32, 8), grid(div_up(dw, 32), div_up(dh, 8));
+    TFB_KT(c, K_RESIZE_MAPS);
     k_resize_points_normals<<<grid, block, 0, c->stream>>>(v, n, vo, no, sw, dw, dh);
     TFB_LAUNCH_CHECK(c);
     return TFB_OK;
