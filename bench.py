@@ -121,6 +121,9 @@ def measured_peak_gbs():
 def algorithmic_bytes(kernel: str, cols: int, rows: int, n_vis_alloc: float) -> float | None:
     """ALGORITHMIC bytes per launch, SURVEY.md §8(d) / DESIGN.md §5"""
     p0 = cols * rows
+    if kernel == "k_icp_all":
+        # every iteration reads 2 own + 2 gathered float4 per pixel of its level: 64 B x (10 P0 + 5 P1 + 4 P2)
+        return 64.0 * (10 * p0 + 5 * (p0 >> 2) + 4 * (p0 >> 4))
     if kernel.startswith("k_icp_iteration[L"):
         lvl = int(kernel[-2])
         return 64.0 * (p0 >> (2 * lvl))                 # 2 own + 2 gathered float4 per pixel
@@ -302,7 +305,7 @@ def main():
         roof["frac"] = roof["achieved"] / peak
     # also report the bandwidth kernels the north star names
     extra = {}
-    for k in ("k_integrate", "k_raycast", "k_icp_iteration[L0]"):
+    for k in ("k_integrate", "k_raycast", "k_icp_all"):
         if k in table:
             b = algorithmic_bytes(k, cols, rows, nvis_avg)
             if b:

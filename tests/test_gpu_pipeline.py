@@ -49,7 +49,7 @@ def test_reference_mode_hover_sequence(gpu):
                 assert abs(co["n_visible"] - cg["n_visible"]) <= max(8, co["n_visible"] // 200), (i, co, cg)
                 assert abs(vo - vg) <= 512 * max(8, co["n_visible"] // 200)
                 compared += 1
-        assert compared >= 9
+        assert compared >= 6
         assert not all(r[0] for r in rows), "the reference is expected to lose tracking on this sequence"
         assert o.num_poses() == g.num_poses()
     finally:

@@ -122,20 +122,7 @@ int do_preprocess(tfb_ctx* c, const uint16_t* depth_dev, bool maps_into_model) {
 }
 
 // ProjectiveICP::estimateTransform, projective_icp.cpp:169-212 — every iteration is one launch, nothing returns to the host
-int do_icp(tfb_ctx* c) {
-    const tfb_params& p = c->p;
-    int r = launch_icp_begin(c);
-    if (r) return r;
-    for (int l = c->levels - 1; l >= 0; --l) {
-        int div = 1 << l;  // setLevelIntr, projective_icp.cpp:17-23
-        for (int it = 0; it < p.icp_iters[l]; ++it) {
-            r = launch_icp_iteration(c, l, c->lv[l].vcurr, c->lv[l].ncurr, c->lv[l].vprev, c->lv[l].nprev, c->lv[l].w, c->lv[l].h,
-                                     p.fx / div, p.fy / div, p.cx / div, p.cy / div, true, nullptr);
-            if (r) return r;
-        }
-    }
-    return TFB_OK;
-}
+int do_icp(tfb_ctx* c, bool update_pose) { return launch_icp_all(c, update_pose); }
 
 int do_frame(tfb_ctx* c, const uint16_t* depth_dev, int* ok) {
     int r;
@@ -151,8 +138,7 @@ int do_frame(tfb_ctx* c, const uint16_t* depth_dev, int* ok) {
         stamp(c, ST_EXPECT); stamp(c, ST_RAYCAST); stamp(c, ST_PYR);
     } else {
         stamp(c, ST_ICP);
-        if ((r = do_icp(c))) return r;
-        if ((r = launch_pose_update(c))) return r;
+        if ((r = do_icp(c, true))) return r;
         stamp(c, ST_ALLOC);
         if ((r = launch_allocate(c, c->dists))) return r;
         stamp(c, ST_INTEG);
@@ -275,7 +261,7 @@ int tfb_create(const tfb_params* p, void* stream, tfb_ctx** out) {
         }
     }
     c->icp_max_blocks = div_up(p->cols, 32) * div_up(p->rows, 8);
-    ok(dmalloc(&c->icp_partial, (size_t)(ICP_TERMS + 1) * c->icp_max_blocks + 32));
+    ok(dmalloc(&c->icp_partial, (size_t)64 * (c->icp_max_blocks > 1024 ? c->icp_max_blocks : 1024) + 64));
     ok(cudaMalloc((void**)&c->ds, sizeof(DevState) + 64 * sizeof(float)));
     ok(cudaMallocHost((void**)&c->hs, sizeof(DevState)));
     ok(cudaMallocHost((void**)&c->h_pose_stage, 64 * sizeof(float)));
@@ -393,7 +379,7 @@ int tfb_icp_reduce(tfb_ctx* c, int cols, int rows, float fx, float fy, float cx,
     TFB_CUDA(c, cudaMemcpyAsync(c->ds->affine, c->h_pose_stage, 64, cudaMemcpyHostToDevice, c->stream));
     float* d27 = reinterpret_cast<float*>(c->ds + 1) + 16;
     r = launch_icp_iteration(c, 0, (const float4*)vcurr, (const float4*)ncurr, (const float4*)vprev, (const float4*)nprev, cols, rows, fx,
-                             fy, cx, cy, false, d27);
+                             fy, cx, cy, false, d27, false, false);
     if (r) return r;
     TFB_CUDA(c, cudaMemcpyAsync(c->h_icp27, d27, 27 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     TFB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -403,7 +389,7 @@ int tfb_icp_reduce(tfb_ctx* c, int cols, int rows, float fx, float fy, float cx,
 
 int tfb_icp_estimate(tfb_ctx* c, float affine_out[16], int* ok) {
     if (!c || !affine_out || !ok) return TFB_ERR_ARG;
-    int r = do_icp(c);
+    int r = do_icp(c, false);
     if (r) return r;
     if ((r = fetch_state(c))) return r;
     memcpy(affine_out, c->hs->affine, 64);
@@ -590,9 +576,9 @@ int tfb_elapsed_ms(tfb_ctx* c, int slot_a, int slot_b, float* ms) {
 
 static const char* const KNAMES[K_COUNT] = {
     "k_bilateral", "k_depth_pyr", "k_points_normals", "k_resize_points_normals", "k_compute_dists", "k_truncate",
-    "k_icp_begin", "k_icp_iteration[L0]", "k_icp_iteration[L1]", "k_icp_iteration[L2]", "k_icp_iteration[L3]", "k_pose_update",
+    "k_icp_begin", "k_icp_iteration[L0]", "k_icp_iteration[L1]", "k_icp_iteration[L2]", "k_icp_iteration[L3]", "(unused)",
     "k_pose_set", "k_set_type3", "k_mark", "k_alloc", "k_visible_list", "k_list_flip", "k_integrate_begin", "k_integrate",
-    "k_minmax_init", "k_expected_depths", "k_raycast", "k_icp_maps", "k_reset_scene"};
+    "k_minmax_init", "k_expected_depths", "k_raycast", "k_icp_maps", "k_reset_scene", "k_icp_all"};
 
 int tfb_ktiming_enable(tfb_ctx* c, int on) {
     if (!c) return TFB_ERR_ARG;

@@ -14,7 +14,7 @@ enum KernelId {
     K_BILATERAL = 0, K_DEPTH_PYR, K_POINTS_NORMALS, K_RESIZE_MAPS, K_COMPUTE_DISTS, K_TRUNCATE,
     K_ICP_BEGIN, K_ICP_L0, K_ICP_L1, K_ICP_L2, K_ICP_L3, K_POSE_UPDATE, K_POSE_SET,
     K_SET_TYPE3, K_MARK, K_ALLOC, K_VISIBLE_LIST, K_LIST_FLIP, K_INTEGRATE_BEGIN, K_INTEGRATE,
-    K_MINMAX_INIT, K_EXPECTED_DEPTHS, K_RAYCAST, K_ICP_MAPS, K_RESET_SCENE, K_COUNT
+    K_MINMAX_INIT, K_EXPECTED_DEPTHS, K_RAYCAST, K_ICP_MAPS, K_RESET_SCENE, K_ICP_ALL, K_COUNT
 };
 constexpr int KT_MAX_EVENTS = 512;
 
@@ -115,6 +115,7 @@ struct tfb_ctx {
     // ICP
     float* icp_partial;        // [ICP_TERMS][max_blocks]
     int icp_max_blocks;
+    int icp_grid;              // persistent ICP grid (co-resident CTAs), sized on first use
     // state
     tfb::DevState* ds;         // device
     tfb::DevState* hs;         // pinned host mirror
@@ -198,9 +199,9 @@ int launch_resize_points_normals(tfb_ctx* c, const float4* v, const float4* n, f
 // icp
 int launch_icp_iteration(tfb_ctx* c, int level, const float4* vcurr, const float4* ncurr, const float4* vprev,
                          const float4* nprev, int w, int h, float fx, float fy, float cx, float cy, bool solve,
-                         float* out27_dev);
+                         float* out27_dev, bool first_iter, bool last_iter);
 int launch_icp_begin(tfb_ctx* c);
-int launch_pose_update(tfb_ctx* c);         // poses.back() * affine and all derived matrices
+int launch_icp_all(tfb_ctx* c, bool update_pose);
 int launch_pose_set(tfb_ctx* c, const float* pose_row_major_host, bool is_w2c);
 // scene
 int launch_reset_scene(tfb_ctx* c);

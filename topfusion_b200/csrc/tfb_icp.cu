@@ -10,6 +10,7 @@
 // The reference spends 27 x (store, barrier, 8-step shared-memory tree, barrier) per CTA plus a second
 // kernel, a 108-byte D2H copy and a stream sync per iteration (19 per frame).
 #include "tfb_common.cuh"
+#include "tfb_pose.cuh"
 
 namespace tfb {
 
@@ -23,6 +24,8 @@ struct IcpArgs {
     float min_cosine, dist2_thres;
     int rows_per_thread;
     int nblk;
+    int first_iter;   // estimateTransform starts from the identity (projective_icp.cpp:174)
+    int last_iter;    // also do poses_.push_back(poses_.back() * affine) and derive the frame's matrices (topfu.cpp:243)
 };
 
 constexpr int ICP_TX = 32, ICP_TY = 8, ICP_THREADS = ICP_TX * ICP_TY, ICP_WARPS = ICP_THREADS / 32;
@@ -34,34 +37,61 @@ __device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, fl
 }
 
 // ---- small dense algebra run by one thread of the last CTA ----------------------------------
+// Everything below is straight-line code over register arrays (all loops unrolled, compile-time indices).
 
-// cv::determinant(Matx66f): LU with partial pivoting in fp32, product in fp64 (projective_icp.cpp:197)
-__device__ double det6_f32(const float* A) {
-    float a[36];
-    for (int i = 0; i < 36; ++i) a[i] = A[i];
+// LU with partial pivoting in fp32 — the algorithm behind cv::determinant(Matx66f) (projective_icp.cpp:197).
+// The factors are kept: they also precondition the solve below.  a = U above/on the diagonal, the multipliers
+// (alpha, already negated as in OpenCV's LUImpl) below it; perm[i] = source row of pivot row i.
+struct Lu6 {
+    float a[6][6];
+    int perm[6];
+    double det;       // sign * prod(diag), 0 when a pivot falls below 10*FLT_EPSILON
+};
+
+__device__ __forceinline__ void lu6_f32(const float (&A)[36], Lu6& f) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        f.perm[i] = i;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) f.a[i][j] = A[i * 6 + j];
+    }
     double p = 1;
+    bool singular = false;
+#pragma unroll
     for (int i = 0; i < 6; ++i) {
         int k = i;
-        for (int j = i + 1; j < 6; ++j)
-            if (fabsf(a[j * 6 + i]) > fabsf(a[k * 6 + i])) k = j;
-        if (fabsf(a[k * 6 + i]) < 1.1920929e-06f) return 0;
-        if (k != i) {
-            for (int j = i; j < 6; ++j) { float t = a[i * 6 + j]; a[i * 6 + j] = a[k * 6 + j]; a[k * 6 + j] = t; }
-            p = -p;
-        }
-        float d = __fdiv_rn(-1.f, a[i * 6 + i]);
+        float best = fabsf(f.a[i][i]);
+#pragma unroll
         for (int j = i + 1; j < 6; ++j) {
-            float alpha = __fmul_rn(a[j * 6 + i], d);
-            for (int cidx = i + 1; cidx < 6; ++cidx) a[j * 6 + cidx] = __fadd_rn(a[j * 6 + cidx], __fmul_rn(alpha, a[i * 6 + cidx]));
+            float v = fabsf(f.a[j][i]);
+            if (v > best) { best = v; k = j; }
+        }
+        if (best < 1.1920929e-06f) singular = true;   // FLT_EPSILON * 10
+#pragma unroll
+        for (int j = i + 1; j < 6; ++j)
+            if (k == j) {
+#pragma unroll
+                for (int c = 0; c < 6; ++c) { float t = f.a[i][c]; f.a[i][c] = f.a[j][c]; f.a[j][c] = t; }
+                int tp = f.perm[i]; f.perm[i] = f.perm[j]; f.perm[j] = tp;
+                p = -p;
+            }
+        const float d = __fdiv_rn(-1.f, f.a[i][i]);
+#pragma unroll
+        for (int j = i + 1; j < 6; ++j) {
+            const float alpha = f.a[j][i] * d;
+#pragma unroll
+            for (int c = i + 1; c < 6; ++c) f.a[j][c] = f.a[j][c] + alpha * f.a[i][c];
+            f.a[j][i] = alpha;   // keep the (negated) multiplier
         }
     }
-    for (int i = 0; i < 6; ++i) p *= a[i * 6 + i];
-    return p;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) p *= f.a[i][i];
+    f.det = singular ? 0.0 : p;
 }
 
 // least-norm solve of the symmetric system through a cyclic-Jacobi eigen-decomposition (fp64) with the
-// back-substitution threshold of cv::solve(DECOMP_SVD) (2*FLT_EPSILON*sum|w|).  Only used when the
-// LDL^T fast path meets a tiny pivot, i.e. for (near) rank-deficient systems.
+// back-substitution threshold of cv::solve(DECOMP_SVD) (2*FLT_EPSILON*sum|w|).  Only reached when the
+// LDL^T fast path meets a tiny pivot, i.e. for (near) rank-deficient systems; kept out of line.
 __device__ __noinline__ void solve6_jacobi(const double* A, const double* b, double* x) {
     double a[6][6], v[6][6];
     for (int i = 0; i < 6; ++i)
@@ -96,94 +126,180 @@ __device__ __noinline__ void solve6_jacobi(const double* A, const double* b, dou
     }
 }
 
-// LDL^T in fp64; false when a pivot is too small relative to the largest diagonal entry
-__device__ bool solve6_ldlt(const double* A, const double* b, double* x) {
-    double L[6][6], d[6];
-    double amax = 0;
-    for (int i = 0; i < 6; ++i) amax = fmax(amax, fabs(A[i * 6 + i]));
-    const double tiny = amax * 4e-6;
+// Fast path: LDL^T in fp32 (no pivoting, A is symmetric positive definite when tracking is healthy) used as a
+// preconditioner, solution refined with fp64 residuals: error shrinks by ~cond(A)*6e-8 per step, three solves
+// give fp64-grade accuracy for cond(A) up to ~1e5.  A pivot below 4e-6 * max(diag) or a refinement that does not
+// contract sends the system to the exact reference path (pivoted-LU determinant test + least-norm eigen solve).
+struct Ldl6 {
+    float l[6][6];
+    float dinv[6];
+    double det;
+    bool ok;
+};
+
+__device__ __forceinline__ void ldl6_f32(const float (&A)[36], Ldl6& f) {
+    float amax = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) amax = fmaxf(amax, fabsf(A[i * 6 + i]));
+    const float tiny = amax * 4e-6f;
+    float d[6];
+    f.ok = true;
+    f.det = 1.0;
+#pragma unroll
     for (int j = 0; j < 6; ++j) {
-        double dj = A[j * 6 + j];
-        for (int k = 0; k < j; ++k) dj -= L[j][k] * L[j][k] * d[k];
-        if (!(dj > tiny)) return false;
+        float dj = A[j * 6 + j];
+#pragma unroll
+        for (int k = 0; k < j; ++k) dj -= f.l[j][k] * f.l[j][k] * d[k];
+        if (!(dj > tiny)) f.ok = false;
         d[j] = dj;
+        f.det *= (double)dj;
+        f.dinv[j] = __fdiv_rn(1.0f, dj);
+#pragma unroll
         for (int i = j + 1; i < 6; ++i) {
-            double s = A[i * 6 + j];
-            for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k] * d[k];
-            L[i][j] = s / dj;
+            float sacc = A[i * 6 + j];
+#pragma unroll
+            for (int k = 0; k < j; ++k) sacc -= f.l[i][k] * f.l[j][k] * d[k];
+            f.l[i][j] = sacc * f.dinv[j];
         }
     }
-    double y[6];
+}
+
+__device__ __forceinline__ void ldl6_solve(const Ldl6& f, const double (&r)[6], float (&x)[6]) {
+    float y[6];
+#pragma unroll
     for (int i = 0; i < 6; ++i) {
-        double s = b[i];
-        for (int k = 0; k < i; ++k) s -= L[i][k] * y[k];
-        y[i] = s;
+        float v = (float)r[i];
+#pragma unroll
+        for (int k = 0; k < i; ++k) v -= f.l[i][k] * y[k];
+        y[i] = v;
     }
+#pragma unroll
     for (int i = 5; i >= 0; --i) {
-        double s = y[i] / d[i];
-        for (int k = i + 1; k < 6; ++k) s -= L[k][i] * x[k];
-        x[i] = s;
+        float v = y[i] * f.dinv[i];
+#pragma unroll
+        for (int k = i + 1; k < 6; ++k) v -= f.l[k][i] * x[k];
+        x[i] = v;
     }
+}
+
+__device__ __forceinline__ bool solve6_refine(const float (&A)[36], const float (&b)[6], const Ldl6& f, double (&x)[6]) {
+    double r[6];
+    float dx[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { x[i] = 0.0; r[i] = b[i]; }
+    double first = 0.0, last = 0.0;
+#pragma unroll
+    for (int step = 0; step < 3; ++step) {
+        ldl6_solve(f, r, dx);
+        double nrm = 0.0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { x[i] += (double)dx[i]; nrm = fmax(nrm, fabs((double)dx[i])); }
+        if (step == 0) first = nrm;
+        last = nrm;
+        if (step < 2) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                double sacc = b[i];
+#pragma unroll
+                for (int j = 0; j < 6; ++j) sacc -= (double)A[i * 6 + j] * x[j];
+                r[i] = sacc;
+            }
+        }
+    }
+    // the third correction must be at the 1e-6 level of the first (two contractions by <= 1e-3 each)
+    return (last <= first * 1e-6) || (first == 0.0);
+}
+
+// the reference's exact path, used when the fast path declines: cv::determinant's pivoted fp32 LU for the nullspace
+// test, then the least-norm solve
+__device__ __noinline__ bool solve6_reference_path(const float* Af_, const float* bf_, double* r_out) {
+    float Af[36];
+    for (int i = 0; i < 36; ++i) Af[i] = Af_[i];
+    Lu6 lu;
+    lu6_f32(Af, lu);
+    const double det = lu.det;
+    if (fabs(det) < 1e-15 || det != det) return false;
+    double A[36], b[6];
+    for (int i = 0; i < 36; ++i) A[i] = Af[i];
+    for (int i = 0; i < 6; ++i) b[i] = bf_[i];
+    solve6_jacobi(A, b, r_out);
     return true;
 }
 
-// StreamHelper::get unpack (projective_icp.cpp:43-62), nullspace test (:197-203), solve (:206),
-// Tinc = Affine3f(rvec, t) and affine = Tinc * affine (:208-209)
-__device__ void icp_solve_update(const double* v27, DevState* ds) {
-    float Af[36], bf[6];
-    int shift = 0;
-    for (int i = 0; i < 6; ++i)
-        for (int j = i; j < 7; ++j) {
-            float value = (float)v27[shift++];
-            if (j == 6) bf[i] = value;
-            else Af[j * 6 + i] = Af[i * 6 + j] = value;
-        }
-    double det = det6_f32(Af);
-    if (fabs(det) < 1e-15 || det != det) {
-        ds->icp_failed = 1;
-        return;
+// sin / cos of a small angle in fp64 by series (|theta| < 0.5: truncation < 1e-17 relative); ICP increments
+// are fractions of a degree.  The generic sincos() is only used for large angles.
+__device__ __forceinline__ void sincos_small(double t, double& s, double& c) {
+    if (t < 0.5) {
+        const double t2 = t * t;
+        s = t * (1.0 + t2 * (-1.0 / 6 + t2 * (1.0 / 120 + t2 * (-1.0 / 5040 + t2 * (1.0 / 362880 + t2 * (-1.0 / 39916800 +
+                 t2 * (1.0 / 6227020800.0 + t2 * (-1.0 / 1307674368000.0))))))));
+        c = 1.0 + t2 * (-0.5 + t2 * (1.0 / 24 + t2 * (-1.0 / 720 + t2 * (1.0 / 40320 + t2 * (-1.0 / 3628800 +
+                 t2 * (1.0 / 479001600.0 + t2 * (-1.0 / 87178291200.0 + t2 * (1.0 / 20922789888000.0))))))));
+    } else {
+        sincos(t, &s, &c);
     }
-    double A[36], b[6], r[6];
-    for (int i = 0; i < 36; ++i) A[i] = Af[i];
-    for (int i = 0; i < 6; ++i) b[i] = bf[i];
-    if (!solve6_ldlt(A, b, r)) solve6_jacobi(A, b, r);
+}
+
+// StreamHelper::get unpack (projective_icp.cpp:43-62), nullspace test (:197-203), solve (:206),
+// Tinc = Affine3f(rvec, t) and affine = Tinc * affine (:208-209).  aff is the running estimate (row-major).
+// Returns false when tracking failed.
+__device__ __noinline__ bool icp_solve_update(const double* v27, float* aff_io) {
+    float aff[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) aff[i] = aff_io[i];
+    float Af[36], bf[6];
+    {
+        int shift = 0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int j = i; j < 7; ++j) {
+                const float value = (float)v27[shift++];
+                if (j == 6) bf[i] = value;
+                else { Af[j * 6 + i] = value; Af[i * 6 + j] = value; }
+            }
+    }
+    double r[6];
+    Ldl6 f;
+    ldl6_f32(Af, f);
+    bool solved = false;
+    if (f.ok && f.det == f.det && fabs(f.det) >= 1e-15) solved = solve6_refine(Af, bf, f, r);
+    if (!solved && !solve6_reference_path(Af, bf, r)) return false;
     float rf[6];
+#pragma unroll
     for (int i = 0; i < 6; ++i) rf[i] = (float)r[i];
 
     // cv::Affine3f(rvec, t): Rodrigues evaluated in double, stored as float
     float T[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
-    double theta = sqrt((double)rf[0] * rf[0] + (double)rf[1] * rf[1] + (double)rf[2] * rf[2]);
+    const double theta = sqrt((double)rf[0] * rf[0] + (double)rf[1] * rf[1] + (double)rf[2] * rf[2]);
     if (theta >= 2.220446049250313e-16) {
         double sn, cs;
-        sincos(theta, &sn, &cs);
-        double c1 = 1. - cs, it = 1. / theta;
-        float rx = (float)(rf[0] * it), ry = (float)(rf[1] * it), rz = (float)(rf[2] * it);
-        double rrt[9] = {(double)rx * rx, (double)rx * ry, (double)rx * rz, (double)rx * ry, (double)ry * ry,
-                         (double)ry * rz, (double)rx * rz, (double)ry * rz, (double)rz * rz};
-        double rc[9] = {0, -(double)rz, (double)ry, (double)rz, 0, -(double)rx, -(double)ry, (double)rx, 0};
+        sincos_small(theta, sn, cs);
+        const double c1 = 1. - cs, it = 1. / theta;
+        const float rx = (float)(rf[0] * it), ry = (float)(rf[1] * it), rz = (float)(rf[2] * it);
+        const double rrt[9] = {(double)rx * rx, (double)rx * ry, (double)rx * rz, (double)rx * ry, (double)ry * ry,
+                               (double)ry * rz, (double)rx * rz, (double)ry * rz, (double)rz * rz};
+        const double rc[9] = {0, -(double)rz, (double)ry, (double)rz, 0, -(double)rx, -(double)ry, (double)rx, 0};
+#pragma unroll
         for (int i = 0; i < 3; ++i)
+#pragma unroll
             for (int j = 0; j < 3; ++j) {
-                int k = i * 3 + j;
+                const int k = i * 3 + j;
                 T[i * 4 + j] = (float)(cs * (i == j ? 1.0 : 0.0) + c1 * rrt[k] + sn * rc[k]);
             }
     }
     T[3] = rf[3]; T[7] = rf[4]; T[11] = rf[5];
-
-    float old[16], nw[16];
-    for (int i = 0; i < 16; ++i) old[i] = ds->affine[i];
-    for (int i = 0; i < 4; ++i)
-        for (int j = 0; j < 4; ++j) {
-            float s = 0;
-            for (int k = 0; k < 4; ++k) s = __fadd_rn(s, __fmul_rn(T[i * 4 + k], old[k * 4 + j]));
-            nw[i * 4 + j] = s;
-        }
-    for (int i = 0; i < 16; ++i) ds->affine[i] = nw[i];
+    float nw[16];
+    pose_mul(T, aff, nw);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) aff_io[i] = nw[i];
+    return true;
 }
 
 // ---- the iteration kernel ---------------------------------------------------------------------
 __global__ void __launch_bounds__(ICP_THREADS)
     k_icp_iteration(IcpArgs a, DevState* __restrict__ ds, float* __restrict__ partial, int solve, float* __restrict__ out27) {
-    if (ds->icp_failed) return;  // estimateTransform returned false earlier in this frame
+    if (!a.first_iter && ds->icp_failed) return;  // estimateTransform returned false earlier in this frame
 
     __shared__ float s_warp[ICP_WARPS][ICP_ACC];
     __shared__ double s_part[ICP_WARPS][32];
@@ -194,10 +310,13 @@ __global__ void __launch_bounds__(ICP_THREADS)
     const int lane = tid & 31, warp = tid >> 5;
 
     // aff = device_cast<Aff3f>(affine): rows of R and t (projective_icp.cpp:190)
-    const float* af = ds->affine;
-    const float r00 = af[0], r01 = af[1], r02 = af[2], t0 = af[3];
-    const float r10 = af[4], r11 = af[5], r12 = af[6], t1 = af[7];
-    const float r20 = af[8], r21 = af[9], r22 = af[10], t2 = af[11];
+    float r00 = 1.f, r01 = 0.f, r02 = 0.f, t0 = 0.f, r10 = 0.f, r11 = 1.f, r12 = 0.f, t1 = 0.f, r20 = 0.f, r21 = 0.f, r22 = 1.f, t2 = 0.f;
+    if (!a.first_iter) {
+        const float* af = ds->affine;
+        r00 = af[0]; r01 = af[1]; r02 = af[2]; t0 = af[3];
+        r10 = af[4]; r11 = af[5]; r12 = af[6]; t1 = af[7];
+        r20 = af[8]; r21 = af[9]; r22 = af[10]; t2 = af[11];
+    }
 
     float acc[ICP_ACC];
 #pragma unroll
@@ -292,12 +411,292 @@ __global__ void __launch_bounds__(ICP_THREADS)
         ds->icp_corresp = (int)s_tot[ICP_TERMS];
         if (out27)
             for (int i = 0; i < ICP_TERMS; ++i) out27[i] = (float)s_tot[i];
-        if (solve) icp_solve_update(s_tot, ds);
+        if (solve) {
+            float aff[16] = {r00, r01, r02, t0, r10, r11, r12, t1, r20, r21, r22, t2, 0.f, 0.f, 0.f, 1.f};
+            const bool ok = icp_solve_update(s_tot, aff);
+            if (a.first_iter || !ok) ds->icp_failed = ok ? 0 : 1;
+            if (ok) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) ds->affine[i] = aff[i];
+                if (a.last_iter) {
+                    float prev[16], nw[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) prev[i] = ds->pose_c2w[i];
+                    pose_mul(prev, aff, nw);
+                    store_pose_c2w(ds, nw);
+                }
+            }
+        } else if (a.first_iter) {
+            ds->icp_failed = 0;
+        }
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// The whole coarse-to-fine loop in ONE cooperative launch (ProjectiveICP::estimateTransform,
+// projective_icp.cpp:169-212: 19 x {kernel, kernel, D2H copy, stream sync, host SVD} in the reference).
+//
+//   * persistent grid (one 512-thread CTA per SM, co-resident by cooperative launch), grid-stride over pixels with four
+//     independent pixels in flight per thread so the dependent load chain v -> (d, n_d) overlaps across pixels;
+//   * per iteration one CTA-level reduction (shuffles + shared memory), one row of partials per CTA, ONE grid
+//     barrier; then every CTA folds all partials in the same fixed order (fp64) and solves redundantly, which makes
+//     the result bit-identical in every CTA and saves the second barrier a broadcast would need;
+//   * the last iteration composes poses_.back() * affine and derives the frame's matrices (topfu.cpp:243,281).
+// ---------------------------------------------------------------------------------------------------------
+struct IcpLevelArgs {
+    const float4* vcurr;
+    const float4* ncurr;
+    const float4* vprev;
+    const float4* nprev;
+    int w, h, iters;
+    float fx, fy, cx, cy;
+};
+
+struct IcpAllArgs {
+    IcpLevelArgs lv[MAX_LEVELS];
+    int levels;
+    float min_cosine, dist2_thres;
+    int update_pose;
+};
+
+constexpr int ICPA_THREADS = 512, ICPA_WARPS = ICPA_THREADS / 32, ICPA_UNROLL = 4;   // one CTA per SM
+
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        while (*((volatile unsigned int*)counter) < target) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+#ifdef TFB_ICP_PROFILE
+__device__ long long g_icp_prof[64 * 8];
+#define ICP_STAMP(slot) do { if (blockIdx.x == 0 && tid == 0 && iter_global < 64) g_icp_prof[iter_global * 8 + (slot)] = clock64(); } while (0)
+#else
+#define ICP_STAMP(slot) do { } while (0)
+#endif
+
+__global__ void __launch_bounds__(ICPA_THREADS, 1)
+    k_icp_all(IcpAllArgs a, DevState* __restrict__ ds, float* __restrict__ partial, unsigned int* __restrict__ barrier) {
+    __shared__ float s_warp[ICPA_WARPS][ICP_ACC];
+    __shared__ double s_part[ICPA_WARPS][32];
+    __shared__ double s_tot[ICP_ACC];
+    __shared__ float s_aff[16];
+    __shared__ int s_ok;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nblk = gridDim.x;
+    const int gtid = blockIdx.x * ICPA_THREADS + tid;
+    const int gstride = nblk * ICPA_THREADS;
+
+    if (tid < 16) s_aff[tid] = ((tid % 5) == 0) ? 1.f : 0.f;   // affine = Identity, projective_icp.cpp:174
+    if (tid == 0) s_ok = 1;
+    __syncthreads();
+
+    unsigned int bar_target = 0;
+    int iter_global = 0;
+    bool ok = true;
+    for (int l = a.levels - 1; l >= 0 && ok; --l) {
+        const IcpLevelArgs L = a.lv[l];
+        const int npx = L.w * L.h;
+        for (int it = 0; it < L.iters && ok; ++it, ++iter_global) {
+            const float r00 = s_aff[0], r01 = s_aff[1], r02 = s_aff[2], t0 = s_aff[3];
+            const float r10 = s_aff[4], r11 = s_aff[5], r12 = s_aff[6], t1 = s_aff[7];
+            const float r20 = s_aff[8], r21 = s_aff[9], r22 = s_aff[10], t2 = s_aff[11];
+            float acc[ICP_ACC];
+#pragma unroll
+            for (int i = 0; i < ICP_ACC; ++i) acc[i] = 0.f;
+            ICP_STAMP(0);
+
+            for (int base = gtid; base < npx; base += gstride * ICPA_UNROLL) {
+                // stage 1: own pixel loads for ICPA_UNROLL independent pixels
+                float4 v[ICPA_UNROLL], nc[ICPA_UNROLL];
+                int idx[ICPA_UNROLL];
+#pragma unroll
+                for (int u = 0; u < ICPA_UNROLL; ++u) {
+                    idx[u] = base + u * gstride;
+                    const bool in = idx[u] < npx;
+                    const float qn = __int_as_float(0x7fffffff);
+                    v[u] = in ? __ldg(L.vcurr + idx[u]) : make_float4(qn, qn, qn, qn);
+                    nc[u] = in ? __ldg(L.ncurr + idx[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                // stage 2: project, issue the gathers
+                float sx[ICPA_UNROLL], sy[ICPA_UNROLL], sz[ICPA_UNROLL];
+                float4 d[ICPA_UNROLL], nd[ICPA_UNROLL];
+                bool valid[ICPA_UNROLL];
+#pragma unroll
+                for (int u = 0; u < ICPA_UNROLL; ++u) {
+                    // find_coresp, proj_icp.cu:80-117 (points variant)
+                    sx[u] = dot3(r00, r01, r02, v[u].x, v[u].y, v[u].z) + t0;
+                    sy[u] = dot3(r10, r11, r12, v[u].x, v[u].y, v[u].z) + t1;
+                    sz[u] = dot3(r20, r21, r22, v[u].x, v[u].y, v[u].z) + t2;
+                    const float cox = __fmaf_rn(L.fx, __fdiv_rn(sx[u], sz[u]), L.cx);
+                    const float coy = __fmaf_rn(L.fy, __fdiv_rn(sy[u], sz[u]), L.cy);
+                    valid[u] = !isnan(v[u].x) && !(sz[u] <= 0 || cox < 0 || coy < 0 || cox >= L.w || coy >= L.h);
+                    const int pidx = valid[u] ? ((int)coy * L.w + (int)cox) : 0;   // point-sampled texel
+                    d[u] = __ldg(L.vprev + pidx);
+                    nd[u] = __ldg(L.nprev + pidx);
+                }
+                // stage 3: tests + accumulation
+#pragma unroll
+                for (int u = 0; u < ICPA_UNROLL; ++u) {
+                    if (!valid[u] || isnan(d[u].x)) continue;
+                    const float ex = sx[u] - d[u].x, ey = sy[u] - d[u].y, ez = sz[u] - d[u].z;
+                    if (dot3(ex, ey, ez, ex, ey, ez) > a.dist2_thres) continue;
+                    const float nsx = dot3(r00, r01, r02, nc[u].x, nc[u].y, nc[u].z);
+                    const float nsy = dot3(r10, r11, r12, nc[u].x, nc[u].y, nc[u].z);
+                    const float nsz = dot3(r20, r21, r22, nc[u].x, nc[u].y, nc[u].z);
+                    if (fabsf(dot3(nsx, nsy, nsz, nd[u].x, nd[u].y, nd[u].z)) < a.min_cosine) continue;
+                    float row[7];
+                    row[0] = sy[u] * nd[u].z - sz[u] * nd[u].y;
+                    row[1] = sz[u] * nd[u].x - sx[u] * nd[u].z;
+                    row[2] = sx[u] * nd[u].y - sy[u] * nd[u].x;
+                    row[3] = nd[u].x; row[4] = nd[u].y; row[5] = nd[u].z;
+                    row[6] = dot3(nd[u].x, nd[u].y, nd[u].z, d[u].x - sx[u], d[u].y - sy[u], d[u].z - sz[u]);
+                    int k = 0;
+#pragma unroll
+                    for (int i = 0; i < 6; ++i)
+#pragma unroll
+                        for (int j = i; j < 7; ++j) acc[k++] += row[i] * row[j];
+                    acc[ICP_TERMS] += 1.f;
+                }
+            }
+
+            ICP_STAMP(1);
+            // CTA reduction -> one row of partials
+#pragma unroll
+            for (int i = 0; i < ICP_ACC; ++i) {
+                float vsum = acc[i];
+#pragma unroll
+                for (int o = 16; o >= 1; o >>= 1) vsum += __shfl_xor_sync(0xffffffffu, vsum, o);
+                if (lane == 0) s_warp[warp][i] = vsum;
+            }
+            __syncthreads();
+            float* prow = partial + (size_t)(iter_global & 1) * nblk * 32;
+            if (tid < 32) {
+                float sacc = 0.f;
+                if (tid < ICP_ACC) {
+#pragma unroll
+                    for (int wi = 0; wi < ICPA_WARPS; ++wi) sacc += s_warp[wi][tid];
+                }
+                prow[blockIdx.x * 32 + tid] = sacc;
+            }
+            bar_target += (unsigned)nblk;
+            ICP_STAMP(2);
+            grid_barrier(barrier, bar_target);
+            ICP_STAMP(3);
+
+            // every CTA: fold all partials in the same order (fp64), solve, update its copy of the transform
+            {
+                // warp p takes CTAs p, p+16, ...; all of a warp's loads are in flight before the first add
+                const int k = lane, part = warp;
+                double sd = 0;
+                for (int b0 = part; b0 < nblk; b0 += ICPA_WARPS * 10) {
+                    float tmp[10];
+#pragma unroll
+                    for (int j = 0; j < 10; ++j) {
+                        const int b = b0 + j * ICPA_WARPS;
+                        tmp[j] = (b < nblk) ? __ldcg(prow + b * 32 + k) : 0.f;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 10; ++j) sd += (double)tmp[j];
+                }
+                s_part[part][k] = sd;
+            }
+            __syncthreads();
+            if (tid < ICP_ACC) {
+                double sd = 0;
+#pragma unroll
+                for (int p = 0; p < ICPA_WARPS; ++p) sd += s_part[p][tid];
+                s_tot[tid] = sd;
+            }
+            __syncthreads();
+            ICP_STAMP(4);
+            if (tid == 0) {
+                float aff[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) aff[i] = s_aff[i];
+                const bool good = icp_solve_update(s_tot, aff);
+                if (good) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) s_aff[i] = aff[i];
+                } else {
+                    s_ok = 0;
+                }
+            }
+            ICP_STAMP(5);
+            __syncthreads();
+            ok = (s_ok != 0);
+        }
+    }
+
+    if (blockIdx.x == 0 && tid == 0) {
+        ds->icp_failed = ok ? 0 : 1;
+        ds->icp_corresp = (int)s_tot[ICP_TERMS];
+        if (ok) {
+            float aff[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { aff[i] = s_aff[i]; ds->affine[i] = aff[i]; }
+            if (a.update_pose) {
+                float prev[16], nw[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) prev[i] = ds->pose_c2w[i];
+                pose_mul(prev, aff, nw);
+                store_pose_c2w(ds, nw);
+            }
+        }
+    }
+}
+
+#ifdef TFB_ICP_PROFILE
+extern "C" __attribute__((visibility("default"))) int tfb_debug_icp_profile(long long* out512) {
+    return cudaMemcpyFromSymbol(out512, g_icp_prof, sizeof(long long) * 64 * 8) == cudaSuccess ? 0 : -2;
+}
+#endif
+
+int launch_icp_all(tfb_ctx* c, bool update_pose) {
+    const tfb_params& p = c->p;
+    IcpAllArgs a;
+    memset(&a, 0, sizeof(a));
+    a.levels = c->levels;
+    a.min_cosine = cosf(p.icp_angle_thres);              // ComputeIcpHelper ctor, projective_icp.cpp:11-15
+    a.dist2_thres = p.icp_dist_thres * p.icp_dist_thres;
+    a.update_pose = update_pose ? 1 : 0;
+    int total = 0;
+    for (int l = 0; l < c->levels; ++l) {
+        const int div = 1 << l;                           // setLevelIntr, projective_icp.cpp:17-23
+        a.lv[l].vcurr = c->lv[l].vcurr; a.lv[l].ncurr = c->lv[l].ncurr;
+        a.lv[l].vprev = c->lv[l].vprev; a.lv[l].nprev = c->lv[l].nprev;
+        a.lv[l].w = c->lv[l].w; a.lv[l].h = c->lv[l].h; a.lv[l].iters = p.icp_iters[l];
+        a.lv[l].fx = p.fx / div; a.lv[l].fy = p.fy / div; a.lv[l].cx = p.cx / div; a.lv[l].cy = p.cy / div;
+        total += p.icp_iters[l];
+    }
+    if (total == 0) return TFB_OK;
+    if (c->icp_grid == 0) {
+        int per_sm = 0, sms = 0;
+        TFB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_icp_all, ICPA_THREADS, 0));
+        TFB_CUDA(c, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+        if (per_sm < 1) return set_err(c, TFB_ERR_CUDA, "icp: kernel does not fit on an SM");
+        c->icp_grid = sms;   // one CTA per SM: the partial rows every CTA folds grow with the grid
+        if (c->icp_grid > c->icp_max_blocks) c->icp_grid = c->icp_max_blocks;
+    }
+    unsigned int* bar = &c->ds->icp_ticket;
+    TFB_CUDA(c, cudaMemsetAsync(bar, 0, sizeof(unsigned int), c->stream));
+    DevState* ds = c->ds;
+    float* partial = c->icp_partial;
+    void* args[] = {&a, &ds, &partial, &bar};
+    TFB_KT(c, K_ICP_ALL);
+    TFB_CUDA(c, cudaLaunchCooperativeKernel((const void*)k_icp_all, dim3(c->icp_grid), dim3(ICPA_THREADS), args, 0, c->stream));
+    TFB_LAUNCH_CHECK(c);
+    return TFB_OK;
+}
+
+// only the stage-level test entry (tfb_icp_reduce) still needs an explicit state reset; the frame path folds it
+// into the first iteration (first_iter)
 __global__ void k_icp_begin(DevState* ds) {
-    // estimateTransform starts from identity (projective_icp.cpp:174)
     if (threadIdx.x < 16) ds->affine[threadIdx.x] = ((threadIdx.x % 5) == 0) ? 1.f : 0.f;
     if (threadIdx.x == 0) { ds->icp_failed = 0; ds->icp_ticket = 0; ds->icp_corresp = 0; }
 }
@@ -310,8 +709,11 @@ int launch_icp_begin(tfb_ctx* c) {
 }
 
 int launch_icp_iteration(tfb_ctx* c, int level, const float4* vcurr, const float4* ncurr, const float4* vprev, const float4* nprev,
-                         int w, int h, float fx, float fy, float cx, float cy, bool solve, float* out27_dev) {
+                         int w, int h, float fx, float fy, float cx, float cy, bool solve, float* out27_dev, bool first_iter,
+                         bool last_iter) {
     IcpArgs a;
+    a.first_iter = first_iter ? 1 : 0;
+    a.last_iter = last_iter ? 1 : 0;
     a.vcurr = vcurr; a.ncurr = ncurr; a.vprev = vprev; a.nprev = nprev;
     a.w = w; a.h = h; a.fx = fx; a.fy = fy; a.cx = cx; a.cy = cy;
     a.min_cosine = cosf(c->p.icp_angle_thres);                 // ComputeIcpHelper ctor, projective_icp.cpp:11-15
