@@ -156,3 +156,34 @@ def test_gpu_launch_counter_and_timing(gpu, s1_frames):
         assert ms["frame"] > 0 and ms["icp"] > 0 and ms["integrate"] > 0
     finally:
         g.close()
+
+
+def test_against_committed_golden_vectors(gpu):
+    """the CUDA path against tests/golden/*.npz (written from the reference-backed oracle/_ref build)"""
+    import glob, os
+    paths = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+    assert paths
+    for path in paths:
+        z = np.load(path)
+        mode, voxel, mu = z["params"]
+        intr = z["intr"]
+        rows, cols = z["depth"].shape[1:]
+        g = gpu.Context(cols=cols, rows=rows, fx=float(intr[0]), fy=float(intr[1]), cx=float(intr[2]), cy=float(intr[3]),
+                        corrected_mode=int(mode), voxel_size=float(voxel), mu=float(mu))
+        try:
+            for i in range(len(z["depth"])):
+                ok = g.process_frame(z["depth"][i])
+                assert ok == bool(z["ok"][i]), (path, i)
+                po = z["est_poses"][i]
+                assert np.abs(po[:3, 3] - g.pose()[:3, 3]).max() < 1e-4, (path, i)
+                assert _rot_angle(po[:3, :3], g.pose()[:3, :3]) < 1e-4, (path, i)
+                nv = int(z["n_visible"][i])
+                assert abs(g.counters()["n_visible"] - nv) <= max(8, nv // 100), (path, i)
+                if i == 0:   # no ICP yet: exact
+                    assert g.voxel_updates() == int(z["voxel_updates"][0])
+            t = g.table()
+            got = {tuple(int(v) for v in p) for p in t[t["ptr"] >= 0]["pos"]}
+            want = {tuple(int(v) for v in p) for p in z["blocks"]}
+            assert len(got ^ want) <= max(8, len(want) // 100), (path, len(got ^ want))
+        finally:
+            g.close()
