@@ -128,6 +128,29 @@ TFB_API int tfb_create_expected_depths(tfb_ctx* c, const float pose_w2c[16]);
 /* CreateICPMaps, VisualisationEngine_CUDA.cu:324-360,474-493: raycast (updates the visible set) + model maps */
 TFB_API int tfb_create_icp_maps(tfb_ctx* c, const float pose_c2w[16], float* points_dev, float* normals_dev);
 
+/* TopFu::renderImage -> RenderImage(RENDER_SHADED_GREYSCALE, RENDER_FROM_NEW_RAYCAST), src/topfu.cpp:332-356,
+ * VisualisationEngine_CUDA.cu:220-291: raycast (visibility untouched) + SDF-gradient shading.  rgba_dev: rows x cols x 4 bytes.
+ * pose_c2w may be NULL to use the context's current camera pose (what the reference does). */
+TFB_API int tfb_render_image(tfb_ctx* c, const float* pose_c2w_or_null, uint8_t* rgba_dev);
+/* ProjectiveICP::estimateTransform(affine, intr, vcurr, ncurr, vprev, nprev) on caller-owned device pyramids
+ * (src/projective_icp.cpp:169-212); level l is (cols >> l) x (rows >> l) float4 maps, intrinsics from the context */
+TFB_API int tfb_icp_estimate_ext(tfb_ctx* c, int levels, const float* const* vcurr, const float* const* ncurr,
+                                 const float* const* vprev, const float* const* nprev, int cols, int rows,
+                                 const int* iters, float dist_thres, float angle_thres, const float intr_or_null[4],
+                                 float affine_out[16], int* ok);
+/* ProjectiveICP::setDistThreshold / setAngleThreshold / setIterationsNum (include/tfusion/cuda/projective_icp.hpp:21-28);
+ * the number of used pyramid levels may not grow beyond what the context was created with */
+TFB_API int tfb_set_icp_params(tfb_ctx* c, float dist_thres, float angle_thres, const int iters[4]);
+/* cuda::getCudaEnabledDeviceCount / getDeviceName / printShortCudaDeviceInfo, src/core.cpp */
+TFB_API int tfb_device_count(void);
+TFB_API int tfb_device_info(int device, char* name, int name_len, int* cc_major, int* cc_minor, int* sm_count, size_t* total_mem);
+/* DeviceMemory2D::upload / download / copyTo with row strides, src/device_memory.cpp:193-250.
+ * kind: 0 host->device (async), 1 device->host (waits), 2 device->device (async) */
+TFB_API int tfb_memcpy_2d(tfb_ctx* c, void* dst, size_t dst_step, const void* src, size_t src_step, size_t width_bytes,
+                          int rows, int kind);
+/* DeviceMemory::copyTo, src/device_memory.cpp */
+TFB_API int tfb_memcpy_d2d(tfb_ctx* c, void* dst_dev, const void* src_dev, size_t bytes);
+
 /* ---- the frame: TopFu::operator(), src/topfu.cpp:161-330 ------------------------------- */
 /* depth_host: rows x cols u16 millimetres with row stride step_bytes (cv::Mat data/step; pinned memory
  * makes the upload asynchronous).  *ok receives operator()'s return value. */

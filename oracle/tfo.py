@@ -72,7 +72,7 @@ class Lib:
         L.tfo_det6.restype = C.c_double
         L.tfo_voxel_updates.restype = C.c_longlong
         for name in ("tfo_destroy", "tfo_reset", "tfo_allocate", "tfo_integrate", "tfo_expected_depths", "tfo_icp_maps",
-                     "tfo_raycast", "tfo_process_frame", "tfo_num_poses", "tfo_get_pose", "tfo_get_counters",
+                     "tfo_raycast", "tfo_render_image", "tfo_process_frame", "tfo_num_poses", "tfo_get_pose", "tfo_get_counters",
                      "tfo_voxel_updates", "tfo_total_entries", "tfo_export_table", "tfo_export_vis_type",
                      "tfo_export_visible_ids", "tfo_export_block", "tfo_export_minmax", "tfo_export_raycast",
                      "tfo_export_dists", "tfo_export_level", "tfo_import_level", "tfo_estimate_transform", "tfo_preprocess"):
@@ -223,6 +223,12 @@ class Oracle:
     def raycast(self, pose_c2w, update_visible=True):
         self.L.lib.tfo_raycast(self.h, _p(_f32(pose_c2w).reshape(16)), C.c_int(1 if update_visible else 0))
         return self.raycast_result()
+
+    def render_image(self, pose_c2w=None):
+        pose = self.pose() if pose_c2w is None else pose_c2w
+        out = np.empty((self.rows, self.cols, 4), np.uint8)
+        self.L.lib.tfo_render_image(self.h, _p(_f32(pose).reshape(16)), _p(out))
+        return out
 
     def process_frame(self, depth) -> bool:
         d = np.ascontiguousarray(depth, dtype=np.uint16)

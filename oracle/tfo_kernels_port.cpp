@@ -416,5 +416,54 @@ void icp_map_pixel(float* points, float* normals, const float* ray, int w, int h
     }
 }
 
+// computeSingleNormalFromSDF (RepresentationAccess.hpp:340-453): per axis A (other axes B, C) the difference of the
+// trilinear SDF one voxel ahead and behind, each face blended in the order (b,c) = (0,0),(1,0),(0,1),(1,1).
+static inline float face(const Voxel* voxels, const HashEntry* table, const HashGeom& g, int ix, int iy, int iz, int axis, int off,
+                         float cB, float cC) {
+    float v[4];
+    for (int i = 0; i < 4; ++i) {
+        int b = i & 1, c = i >> 1;
+        int d[3];
+        if (axis == 0) { d[0] = off; d[1] = b; d[2] = c; }
+        else if (axis == 1) { d[0] = b; d[1] = off; d[2] = c; }
+        else { d[0] = b; d[1] = c; d[2] = off; }
+        int found; BlockCache fresh;
+        v[i] = (float)read_voxel(voxels, table, ix + d[0], iy + d[1], iz + d[2], found, fresh, g).sdf;
+    }
+    float nB = 1.0f - cB, nC = 1.0f - cC;
+    return v[0] * nB * nC + v[1] * cB * nC + v[2] * nB * cC + v[3] * cB * cC;
+}
+
+// processPixelGrey + computeNormalAndAngle<TVoxel,TIndex> + drawPixelGrey (VisualisationEngine_Shared.hpp:189-203,272-276,450-462)
+void shade_pixel_grey(uint8_t out[4], const float ray[4], const Voxel* voxels, const HashEntry* table, const float light[3],
+                      const HashGeom& g) {
+    bool ok = ray[3] > 0;
+    float ang = 0.f;
+    if (ok) {
+        float f[3] = {floorf(ray[0]), floorf(ray[1]), floorf(ray[2])};
+        float c[3] = {ray[0] - f[0], ray[1] - f[1], ray[2] - f[2]};
+        int ix = (int)f[0], iy = (int)f[1], iz = (int)f[2];
+        float n[3];
+        for (int axis = 0; axis < 3; ++axis) {
+            float cA = c[axis], nA = 1.0f - cA;
+            float cB = (axis == 0) ? c[1] : c[0];
+            float cC = (axis == 2) ? c[1] : c[2];
+            float p1 = face(voxels, table, g, ix, iy, iz, axis, 0, cB, cC);
+            float p2 = face(voxels, table, g, ix, iy, iz, axis, -1, cB, cC);
+            float v1 = p1 * cA + p2 * nA;
+            p1 = face(voxels, table, g, ix, iy, iz, axis, 1, cB, cC);
+            p2 = face(voxels, table, g, ix, iy, iz, axis, 2, cB, cC);
+            n[axis] = (p1 * nA + p2 * cA - v1) / 32767.0f;
+        }
+        float sc = 1.0f / sqrtf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+        n[0] *= sc; n[1] *= sc; n[2] *= sc;
+        ang = n[0] * light[0] + n[1] * light[1] + n[2] * light[2];
+        if (!(ang > 0.0)) ok = false;
+    }
+    uint8_t v = 0;
+    if (ok) v = (uint8_t)((0.8f * ang + 0.2f) * 255.0f);
+    out[0] = out[1] = out[2] = out[3] = v;
+}
+
 }  // namespace k
 }  // namespace tfo

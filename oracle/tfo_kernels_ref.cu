@@ -109,6 +109,15 @@ void icp_map_pixel(float* points, float* normals, const float* ray, int w, int h
     }
 }
 
+void shade_pixel_grey(uint8_t out[4], const float ray[4], const Voxel* voxels, const HashEntry* table, const float light[3],
+                      const HashGeom& g) {
+    check_geom(g);
+    Vector4u px;
+    Vector3f pt(ray[0], ray[1], ray[2]), l(light[0], light[1], light[2]);
+    processPixelGrey<Voxel_s, tfusion::VoxelBlockHash>(px, pt, ray[3] > 0, (const Voxel_s*)voxels, (const ::HashEntry*)table, l);
+    out[0] = px.x; out[1] = px.y; out[2] = px.z; out[3] = px.w;
+}
+
 }  // namespace k
 }  // namespace tfo
 

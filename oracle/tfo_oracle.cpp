@@ -652,6 +652,19 @@ struct Oracle {
         }
     }
 
+    // TopFu::renderImage -> RenderImage_common(RENDER_SHADED_GREYSCALE, RENDER_FROM_NEW_RAYCAST)
+    // (topfu.cpp:332-356, VisualisationEngine_CUDA.cu:220-291): raycast without touching visibility, then renderGrey_device
+    void render_image(const Pose& pose_c2w, uint8_t* out_rgba) {
+        raycast_pass(pose_c2w, false);
+        float light[3] = {-pose_c2w.m[2], -pose_c2w.m[6], -pose_c2w.m[10]};
+#pragma omp parallel for schedule(dynamic, 4)
+        for (int y = 0; y < p.rows; ++y)
+            for (int x = 0; x < p.cols; ++x) {
+                size_t id = (size_t)x + (size_t)y * p.cols;
+                k::shade_pixel_grey(out_rgba + 4 * id, &raycast[4 * id], vba.data(), table.data(), light, g);
+            }
+    }
+
     // ProjectiveICP::estimateTransform (points variant), projective_icp.cpp:169-212
     bool estimate_transform(Pose& affine) {
         IcpSetup s;
@@ -779,6 +792,7 @@ void tfo_allocate(void* h, const float* pose_w2c, const float* dists) { Pose p; 
 void tfo_integrate(void* h, const float* pose_w2c, const float* dists) { Pose p; memcpy(p.m, pose_w2c, 64); ((Oracle*)h)->integrate(p, dists); }
 void tfo_expected_depths(void* h, const float* pose_w2c) { Pose p; memcpy(p.m, pose_w2c, 64); ((Oracle*)h)->expected_depths(p); }
 void tfo_icp_maps(void* h, const float* pose_c2w, float* points, float* normals) { Pose p; memcpy(p.m, pose_c2w, 64); ((Oracle*)h)->icp_maps(p, points, normals); }
+void tfo_render_image(void* h, const float* pose_c2w, uint8_t* out_rgba) { Pose p; memcpy(p.m, pose_c2w, 64); ((Oracle*)h)->render_image(p, out_rgba); }
 void tfo_raycast(void* h, const float* pose_c2w, int update_visible) { Pose p; memcpy(p.m, pose_c2w, 64); ((Oracle*)h)->raycast_pass(p, update_visible != 0); }
 
 // full frame

@@ -105,5 +105,8 @@ bool cast_ray(float out[4], uint8_t* vis_type, int x, int y, const Voxel* voxels
               float one_over_voxel, float mu, const float minmax[2], const HashGeom& g);
 void icp_map_pixel(float* points, float* normals, const float* ray, int w, int h, int x, int y,
                    float voxel_size, const float light[3]);
+// processPixelGrey<Voxel_s, VoxelBlockHash>: SDF-gradient normal + Lambert shade of one raycast point (viewer path)
+void shade_pixel_grey(uint8_t out[4], const float ray[4], const Voxel* voxels, const HashEntry* table,
+                      const float light[3], const HashGeom& g);
 }  // namespace k
 }  // namespace tfo

@@ -173,3 +173,14 @@ def test_pool_exhaustion_restores_counters(gpu, s1_frames):
         assert (t["ptr"] >= 0).sum() == 500
     finally:
         g.close()
+
+
+def test_viewer_render_bit_exact(both):
+    """TopFu::renderImage (RENDER_SHADED_GREYSCALE from a new raycast): SDF-gradient normals, 32 voxel reads per pixel"""
+    o, g, _, _ = both
+    pose = o.L.pose_inv(np.eye(4, dtype=np.float32))
+    vis_before = g.vis_type().copy()
+    io, ig = o.render_image(pose), g.render_image(pose)
+    assert (io[..., 0] > 0).mean() > 0.2
+    assert np.array_equal(io, ig)
+    assert np.array_equal(vis_before, g.vis_type()), "renderImage must not touch the visible set (updateVisibleList=false)"

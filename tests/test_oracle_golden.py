@@ -37,7 +37,9 @@ def test_full_pipeline_matches_reference_vectors(path, oracle_lib):
             assert np.array_equal(o.pose().view(np.uint32), z["est_poses"][i].view(np.uint32)), f"pose of frame {i}"
             assert o.counters()["n_visible"] == z["n_visible"][i]
             assert o.voxel_updates() == z["voxel_updates"][i]
-            if i == 1:
+            if i == 1 and "f1_model_points_sha" in z:
+                assert digest(o.level(3, 0)) == str(z["f1_model_points_sha"])
+            elif i == 1:
                 a, b = o.level(3, 0), z["f1_model_points"]
                 assert np.array_equal(np.isnan(a), np.isnan(b))
                 assert np.array_equal(a[~np.isnan(a)].view(np.uint32), b[~np.isnan(b)].view(np.uint32))
@@ -55,7 +57,7 @@ def test_full_pipeline_matches_reference_vectors(path, oracle_lib):
         o.close()
 
 
-@pytest.mark.parametrize("path", GOLDEN[:1])
+@pytest.mark.parametrize("path", [p for p in GOLDEN if "160x120_reference_mode" in p])
 def test_stage_vectors(path, oracle_lib):
     z = np.load(path)
     L = oracle_lib

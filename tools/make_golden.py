@@ -30,7 +30,7 @@ def scene_digest(o) -> dict:
             "sdf_sum": int(vox["sdf"].astype(np.int64).sum()), "w_sum": int(vox["w"].astype(np.int64).sum())}
 
 
-def run(name, seq, cols, rows, n, **kw):
+def run(name, seq, cols, rows, n, lite=False, **kw):
     assert tfo.have_ref(), "build oracle/_ref first (make -C oracle)"
     L = tfo.Lib("ref")
     assert L.impl_name() == "reference"
@@ -42,7 +42,10 @@ def run(name, seq, cols, rows, n, **kw):
         oks.append(o.process_frame(depth[i]))
         est.append(o.pose().copy()); nvis.append(o.counters()["n_visible"]); vupd.append(o.voxel_updates())
         if i == 1:
-            out["f1_model_points"] = o.level(3, 0)
+            if lite:
+                out["f1_model_points_sha"] = digest(o.level(3, 0))
+            else:
+                out["f1_model_points"] = o.level(3, 0)
             out["f1_raycast_sha"] = digest(o.raycast_result())
     out.update(est_poses=np.stack(est), ok=np.array(oks), n_visible=np.array(nvis), voxel_updates=np.array(vupd))
     sd = scene_digest(o)
@@ -50,6 +53,12 @@ def run(name, seq, cols, rows, n, **kw):
     out["raycast_sha"] = digest(o.raycast_result())
     out["vis_ids_sorted"] = np.sort(o.visible_ids())
     out["params"] = np.array([kw.get("corrected_mode", 0), kw.get("voxel_size", 0.005), kw.get("mu", 0.02)], np.float64)
+    path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    if lite:   # full-resolution fixture: frames + per-frame results + digests only
+        np.savez_compressed(path, **out)
+        print(name, "->", path, os.path.getsize(path) // 1024, "KiB; blocks", len(sd["blocks"]), "ok", oks, "nvis", nvis)
+        o.close()
+        return
     # stage-level vectors for frame 0/1 inputs
     d0 = depth[0]
     out["st_dists_sha"] = digest(L.compute_dists(d0))
@@ -60,7 +69,6 @@ def run(name, seq, cols, rows, n, **kw):
     aff = L.rodrigues([0.001, -0.002, 0.0015], [0.003, -0.001, 0.002])
     v27, nc = L.icp_reduce(intr, aff, p1, n1, pts, nrm)
     out["st_icp_aff"] = aff; out["st_icp27"] = v27; out["st_icp_ncorr"] = nc
-    path = os.path.join(ROOT, "tests", "golden", name + ".npz")
     np.savez_compressed(path, **out)
     print(name, "->", path, os.path.getsize(path) // 1024, "KiB; blocks", len(sd["blocks"]), "ok", oks, "nvis", nvis)
     o.close()
@@ -70,3 +78,5 @@ if __name__ == "__main__":
     run("s1_160x120_reference_mode", "S1", 160, 120, 5)
     run("s1_160x120_corrected_mode", "S1", 160, 120, 6, corrected_mode=1)
     run("s0_160x120_reference_8mm", "S0", 160, 120, 4, voxel_size=0.008)
+    # full resolution: the only size at which frame-to-frame ICP is stiff enough for a 1e-4 GPU-vs-golden pose bound
+    run("s1_640x480_corrected_mode", "S1", 640, 480, 3, lite=True, corrected_mode=1)

@@ -293,6 +293,13 @@ class Context:
         return (self.download(pts, (self.rows, self.cols, 4), np.float32),
                 self.download(nrm, (self.rows, self.cols, 4), np.float32))
 
+    def render_image(self, pose_c2w=None):
+        """TopFu::renderImage: shaded greyscale view, uint8 [rows, cols, 4]"""
+        out = DevBuf(self.rows * self.cols * 4)
+        p = _np_ptr(_f32(pose_c2w).reshape(16)) if pose_c2w is not None else None
+        self._ck(self.L.tfb_render_image(self.h, p, out.ptr))
+        return self.download(out, (self.rows, self.cols, 4), np.uint8)
+
     # -- frames ----------------------------------------------------------------------------------------
     def process_frame(self, depth) -> bool:
         """depth: host u16 [rows, cols]; a PinnedArray's .array makes the upload asynchronous."""

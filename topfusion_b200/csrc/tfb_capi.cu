@@ -427,6 +427,69 @@ int tfb_create_icp_maps(tfb_ctx* c, const float pose_c2w[16], float* points_dev,
     return launch_icp_maps(c, (float4*)points_dev, (float4*)normals_dev);
 }
 
+int tfb_render_image(tfb_ctx* c, const float* pose_c2w_or_null, uint8_t* rgba_dev) {
+    if (!c || !rgba_dev) return TFB_ERR_ARG;
+    if (pose_c2w_or_null) {
+        int r = launch_pose_set(c, pose_c2w_or_null, false);
+        if (r) return r;
+    }
+    return launch_render_grey(c, (uchar4*)rgba_dev);
+}
+
+int tfb_icp_estimate_ext(tfb_ctx* c, int levels, const float* const* vcurr, const float* const* ncurr, const float* const* vprev,
+                         const float* const* nprev, int cols, int rows, const int* iters, float dist_thres, float angle_thres,
+                         const float intr_or_null[4], float affine_out[16], int* ok) {
+    if (!c || !vcurr || !ncurr || !vprev || !nprev || !iters || !affine_out || !ok) return TFB_ERR_ARG;
+    tfb_params saved = c->p;
+    if (intr_or_null) { c->p.fx = intr_or_null[0]; c->p.fy = intr_or_null[1]; c->p.cx = intr_or_null[2]; c->p.cy = intr_or_null[3]; }
+    int r = launch_icp_all_ext(c, levels, vcurr, ncurr, vprev, nprev, cols, rows, iters, dist_thres, angle_thres);
+    c->p = saved;
+    if (r) return r;
+    if ((r = fetch_state(c))) return r;
+    memcpy(affine_out, c->hs->affine, 64);
+    *ok = c->hs->icp_failed ? 0 : 1;
+    return TFB_OK;
+}
+
+int tfb_set_icp_params(tfb_ctx* c, float dist_thres, float angle_thres, const int iters[4]) {
+    if (!c || !iters) return TFB_ERR_ARG;
+    tfb_params q = c->p;
+    for (int i = 0; i < 4; ++i) q.icp_iters[i] = iters[i];
+    if (used_levels(q) > MAX_LEVELS || used_levels(q) < 1) return TFB_ERR_ARG;
+    c->p.icp_dist_thres = dist_thres;
+    c->p.icp_angle_thres = angle_thres;
+    for (int i = 0; i < 4; ++i) c->p.icp_iters[i] = iters[i];
+    c->levels = used_levels(c->p);
+    return TFB_OK;
+}
+
+int tfb_device_count(void) {
+    int n = 0;
+    return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
+int tfb_device_info(int device, char* name, int name_len, int* cc_major, int* cc_minor, int* sm_count, size_t* total_mem) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, device) != cudaSuccess) return TFB_ERR_CUDA;
+    if (name && name_len > 0) { strncpy(name, p.name, (size_t)name_len - 1); name[name_len - 1] = 0; }
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (total_mem) *total_mem = p.totalGlobalMem;
+    return TFB_OK;
+}
+int tfb_memcpy_2d(tfb_ctx* c, void* dst, size_t dst_step, const void* src, size_t src_step, size_t width_bytes, int rows, int kind) {
+    if (!c || !dst || !src || rows < 0 || kind < 0 || kind > 2) return TFB_ERR_ARG;
+    const cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice : (kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice);
+    TFB_CUDA(c, cudaMemcpy2DAsync(dst, dst_step, src, src_step, width_bytes, (size_t)rows, k, c->stream));
+    if (kind != 2) TFB_CUDA(c, cudaStreamSynchronize(c->stream));   // host buffers may be pageable / reused
+    return TFB_OK;
+}
+int tfb_memcpy_d2d(tfb_ctx* c, void* dst, const void* src, size_t bytes) {
+    if (!c || !dst || !src) return TFB_ERR_ARG;
+    TFB_CUDA(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    return TFB_OK;
+}
+
 // ---- the frame ----------------------------------------------------------------------------------------
 int tfb_process_frame(tfb_ctx* c, const uint16_t* depth_host, size_t step_bytes, int* ok) {
     if (!c || !depth_host || !ok) return TFB_ERR_ARG;
@@ -578,7 +641,7 @@ static const char* const KNAMES[K_COUNT] = {
     "k_bilateral", "k_depth_pyr", "k_points_normals", "k_resize_points_normals", "k_compute_dists", "k_truncate",
     "k_icp_begin", "k_icp_iteration[L0]", "k_icp_iteration[L1]", "k_icp_iteration[L2]", "k_icp_iteration[L3]", "(unused)",
     "k_pose_set", "k_set_type3", "k_mark", "k_alloc", "k_visible_list", "k_list_flip", "k_integrate_begin", "k_integrate",
-    "k_minmax_init", "k_expected_depths", "k_raycast", "k_icp_maps", "k_reset_scene", "k_icp_all"};
+    "k_minmax_init", "k_expected_depths", "k_raycast", "k_icp_maps", "k_reset_scene", "k_icp_all", "k_render_grey"};
 
 int tfb_ktiming_enable(tfb_ctx* c, int on) {
     if (!c) return TFB_ERR_ARG;

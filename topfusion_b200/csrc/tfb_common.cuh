@@ -14,7 +14,7 @@ enum KernelId {
     K_BILATERAL = 0, K_DEPTH_PYR, K_POINTS_NORMALS, K_RESIZE_MAPS, K_COMPUTE_DISTS, K_TRUNCATE,
     K_ICP_BEGIN, K_ICP_L0, K_ICP_L1, K_ICP_L2, K_ICP_L3, K_POSE_UPDATE, K_POSE_SET,
     K_SET_TYPE3, K_MARK, K_ALLOC, K_VISIBLE_LIST, K_LIST_FLIP, K_INTEGRATE_BEGIN, K_INTEGRATE,
-    K_MINMAX_INIT, K_EXPECTED_DEPTHS, K_RAYCAST, K_ICP_MAPS, K_RESET_SCENE, K_ICP_ALL, K_COUNT
+    K_MINMAX_INIT, K_EXPECTED_DEPTHS, K_RAYCAST, K_ICP_MAPS, K_RESET_SCENE, K_ICP_ALL, K_RENDER_GREY, K_COUNT
 };
 constexpr int KT_MAX_EVENTS = 512;
 
@@ -202,6 +202,8 @@ int launch_icp_iteration(tfb_ctx* c, int level, const float4* vcurr, const float
                          float* out27_dev, bool first_iter, bool last_iter);
 int launch_icp_begin(tfb_ctx* c);
 int launch_icp_all(tfb_ctx* c, bool update_pose);
+int launch_icp_all_ext(tfb_ctx* c, int levels, const float* const* vcurr, const float* const* ncurr, const float* const* vprev,
+                       const float* const* nprev, int cols, int rows, const int* iters, float dist_thres, float angle_thres);
 int launch_pose_set(tfb_ctx* c, const float* pose_row_major_host, bool is_w2c);
 // scene
 int launch_reset_scene(tfb_ctx* c);
@@ -210,5 +212,7 @@ int launch_integrate(tfb_ctx* c, const float* dists);
 // vis
 int launch_expected_depths(tfb_ctx* c);
 int launch_icp_maps(tfb_ctx* c, float4* points, float4* normals);
+int launch_render_grey(tfb_ctx* c, uchar4* out);
+int launch_raycast(tfb_ctx* c, bool update_visible);
 
 }  // namespace tfb

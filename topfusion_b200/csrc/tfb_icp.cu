@@ -657,6 +657,31 @@ extern "C" __attribute__((visibility("default"))) int tfb_debug_icp_profile(long
 }
 #endif
 
+static int launch_icp_args(tfb_ctx* c, IcpAllArgs& a, int total);
+
+// ProjectiveICP::estimateTransform on caller-owned pyramids (projective_icp.cpp:169-212), for the C++ ProjectiveICP class
+int launch_icp_all_ext(tfb_ctx* c, int levels, const float* const* vcurr, const float* const* ncurr, const float* const* vprev,
+                       const float* const* nprev, int cols, int rows, const int* iters, float dist_thres, float angle_thres) {
+    if (levels < 1 || levels > MAX_LEVELS) return set_err(c, TFB_ERR_ARG, "icp: 1..4 pyramid levels");
+    IcpAllArgs a;
+    memset(&a, 0, sizeof(a));
+    a.levels = levels;
+    a.min_cosine = cosf(angle_thres);
+    a.dist2_thres = dist_thres * dist_thres;
+    a.update_pose = 0;
+    int total = 0, w = cols, h = rows;
+    for (int l = 0; l < levels; ++l) {
+        const int div = 1 << l;
+        a.lv[l].vcurr = (const float4*)vcurr[l]; a.lv[l].ncurr = (const float4*)ncurr[l];
+        a.lv[l].vprev = (const float4*)vprev[l]; a.lv[l].nprev = (const float4*)nprev[l];
+        a.lv[l].w = w; a.lv[l].h = h; a.lv[l].iters = iters[l];
+        a.lv[l].fx = c->p.fx / div; a.lv[l].fy = c->p.fy / div; a.lv[l].cx = c->p.cx / div; a.lv[l].cy = c->p.cy / div;
+        total += iters[l];
+        w /= 2; h /= 2;
+    }
+    return launch_icp_args(c, a, total);
+}
+
 int launch_icp_all(tfb_ctx* c, bool update_pose) {
     const tfb_params& p = c->p;
     IcpAllArgs a;
@@ -674,6 +699,10 @@ int launch_icp_all(tfb_ctx* c, bool update_pose) {
         a.lv[l].fx = p.fx / div; a.lv[l].fy = p.fy / div; a.lv[l].cx = p.cx / div; a.lv[l].cy = p.cy / div;
         total += p.icp_iters[l];
     }
+    return launch_icp_args(c, a, total);
+}
+
+static int launch_icp_args(tfb_ctx* c, IcpAllArgs& a, int total) {
     if (total == 0) return TFB_OK;
     if (c->icp_grid == 0) {
         int per_sm = 0, sms = 0;
