@@ -1,0 +1,29 @@
+#!/usr/bin/env python
+"""Summarise an .ncu-rep (read here, on the CPU box) into a small CSV for profiles/:
+one row per profiled launch with duration, DRAM bytes, hit rates, occupancy, registers."""
+import csv
+import subprocess
+import sys
+
+WANT = ["Kernel Name", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+        "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
+        "l1tex__t_sector_hit_rate.pct", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "smsp__average_warp_latency_per_inst_issued.ratio", "smsp__thread_inst_executed_per_inst_executed.ratio"]
+
+
+def main(rep, out):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    idx = [(w, hdr.index(w)) for w in WANT if w in hdr]
+    with open(out, "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow([f"{n} [{units[i]}]" if units[i] else n for n, i in idx])
+        for r in rows[2:]:
+            w.writerow([r[i].split("(")[0] if n == "Kernel Name" else r[i] for n, i in idx])
+
+
+if __name__ == "__main__":
+    main(sys.argv[1], sys.argv[2])
