@@ -161,6 +161,40 @@ TFB_API int tfb_process_frame_device(tfb_ctx* c, const uint16_t* depth_dev, int*
 TFB_API int tfb_get_pose(const tfb_ctx* c, int time, float out16[16]);
 TFB_API int tfb_num_poses(const tfb_ctx* c);
 
+/* ---- scene sharded across GPUs (new: the reference is single-GPU) ---------------
+ * One context per GPU (one process per GPU), created with shard_rank / shard_count.  The hash INDEX is replicated
+ * (every rank sees every frame and takes the same allocation decisions); the 2 KB voxel payload of a block lives
+ * only in the pool of its owner (a mix of the block coordinate).  A frame runs in three stages with a cross-GPU
+ * barrier on the context stream between them (the caller supplies it: an NCCL all-reduce on the same stream):
+ *
+ *   tfb_frame_begin    preprocess + ICP + allocation (replicated), integration of this rank's blocks (no exchange)
+ *   -- barrier --
+ *   tfb_frame_raycast  expected depths; this rank casts its 8-row strips (strip % shard_count == shard_rank) and reads
+ *                      the voxels of foreign blocks straight out of the owner's table + pool over NVLink peer memory;
+ *                      finished rows and visibility marks are stored into EVERY rank's buffers by the same kernel
+ *   -- barrier --
+ *   tfb_frame_end      incoming visibility marks, model maps, map pyramid, state read-back (operator()'s verdict)
+ *
+ * The march of every ray is the single-GPU march, so the result is identical to one context holding the whole scene.
+ * Peer buffers are attached as plain device pointers valid in the calling process: another context's pointers on the
+ * same device (single-process emulation, tests) or pointers opened from CUDA IPC handles (one process per GPU). */
+#define TFB_MAX_SHARDS 16
+typedef struct tfb_shard_ptrs {
+    void* table;     /* total_entries x 16 B hash entries */
+    void* vba;       /* num_blocks x 2 KB voxel pool */
+    void* raycast;   /* rows x cols float4 raycast result */
+    void* marks;     /* incoming visibility marks: u32 count, pad, then 2 x u32 per mark */
+} tfb_shard_ptrs;
+TFB_API int tfb_shard_local_ptrs(tfb_ctx* c, tfb_shard_ptrs* out);
+TFB_API int tfb_shard_attach(tfb_ctx* c, int rank, const tfb_shard_ptrs* peer);
+TFB_API int tfb_ipc_export(const void* dev_ptr, unsigned char handle64[64]);   /* cudaIpcGetMemHandle */
+TFB_API int tfb_ipc_open(const unsigned char handle64[64], void** dev_ptr);    /* cudaIpcOpenMemHandle, peer access enabled */
+TFB_API int tfb_ipc_close(void* dev_ptr);
+TFB_API int tfb_frame_begin(tfb_ctx* c, const uint16_t* depth_dev);
+TFB_API int tfb_frame_raycast(tfb_ctx* c);
+TFB_API int tfb_frame_end(tfb_ctx* c, int* ok);
+TFB_API void* tfb_stream(tfb_ctx* c);   /* the cudaStream_t the context runs on */
+
 /* ---- inspection (tests, bench, debug dumps) ---------------------------------------------- */
 /* out[8] = n_visible, last_free_block, last_free_excess, n_new_this_frame, frame_counter, resets,
  *          n_raycast_extras, n_allocated */

@@ -38,6 +38,11 @@ class Params(C.Structure):
     ]
 
 
+class ShardPtrs(C.Structure):
+    """tfb_shard_ptrs: the buffers of one rank that the other ranks read / write over peer memory"""
+    _fields_ = [("table", C.c_void_p), ("vba", C.c_void_p), ("raycast", C.c_void_p), ("marks", C.c_void_p)]
+
+
 class TfbError(RuntimeError):
     pass
 
@@ -67,6 +72,7 @@ def lib() -> C.CDLL:
         L.tfb_kernel_launches.restype = C.c_longlong
         L.tfb_level_ptr.restype = C.c_void_p
         L.tfb_ktiming_name.restype = C.c_char_p
+        L.tfb_stream.restype = C.c_void_p
         for name, args in {
             "tfb_create": [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)],
             "tfb_dev_alloc": [C.POINTER(C.c_void_p), C.c_size_t],
@@ -78,6 +84,15 @@ def lib() -> C.CDLL:
             "tfb_process_frame": [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int)],
             "tfb_process_frame_device": [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)],
             "tfb_level_ptr": [C.c_void_p, C.c_int, C.c_int],
+            "tfb_stream": [C.c_void_p],
+            "tfb_shard_local_ptrs": [C.c_void_p, C.POINTER(ShardPtrs)],
+            "tfb_shard_attach": [C.c_void_p, C.c_int, C.POINTER(ShardPtrs)],
+            "tfb_ipc_export": [C.c_void_p, C.c_char_p],
+            "tfb_ipc_open": [C.c_char_p, C.POINTER(C.c_void_p)],
+            "tfb_ipc_close": [C.c_void_p],
+            "tfb_frame_begin": [C.c_void_p, C.c_void_p],
+            "tfb_frame_raycast": [C.c_void_p],
+            "tfb_frame_end": [C.c_void_p, C.POINTER(C.c_int)],
         }.items():
             getattr(L, name).argtypes = args
         _lib = L
@@ -315,6 +330,30 @@ class Context:
         self._ck(self.L.tfb_process_frame_device(self.h, p, C.byref(ok)))
         return bool(ok.value)
 
+    # -- sharded scene: the frame in three stages, a cross-GPU barrier on the stream between them -------
+    def stream(self) -> int:
+        return int(self.L.tfb_stream(self.h) or 0)
+
+    def shard_local_ptrs(self) -> ShardPtrs:
+        p = ShardPtrs()
+        self._ck(self.L.tfb_shard_local_ptrs(self.h, C.byref(p)))
+        return p
+
+    def shard_attach(self, rank: int, ptrs: ShardPtrs):
+        self._ck(self.L.tfb_shard_attach(self.h, C.c_int(rank), C.byref(ptrs)))
+
+    def frame_begin(self, dev_ptr):
+        p = dev_ptr.ptr if isinstance(dev_ptr, DevBuf) else C.c_void_p(dev_ptr)
+        self._ck(self.L.tfb_frame_begin(self.h, p))
+
+    def frame_raycast(self):
+        self._ck(self.L.tfb_frame_raycast(self.h))
+
+    def frame_end(self) -> bool:
+        ok = C.c_int(0)
+        self._ck(self.L.tfb_frame_end(self.h, C.byref(ok)))
+        return bool(ok.value)
+
     def num_poses(self) -> int:
         return int(self.L.tfb_num_poses(self.h))
 
@@ -429,6 +468,22 @@ class Context:
         t = np.zeros(9, np.float32)
         self._ck(self.L.tfb_timing_last_ms(self.h, _np_ptr(t)))
         return dict(zip(STAGES, (float(v) for v in t)))
+
+
+def ipc_export(ptr: int) -> bytes:
+    """cudaIpcGetMemHandle of a device allocation of this process (64 opaque bytes to send to the other ranks)"""
+    buf = C.create_string_buffer(64)
+    if lib().tfb_ipc_export(C.c_void_p(ptr), buf) != 0:
+        raise TfbError("cudaIpcGetMemHandle failed")
+    return buf.raw
+
+
+def ipc_open(handle: bytes) -> int:
+    """cudaIpcOpenMemHandle: a pointer, valid in this process, to another rank's allocation (peer access enabled)"""
+    out = C.c_void_p()
+    if lib().tfb_ipc_open(C.create_string_buffer(handle, 64), C.byref(out)) != 0:
+        raise TfbError("cudaIpcOpenMemHandle failed (are the GPUs peer-accessible?)")
+    return int(out.value)
 
 
 def allocated_set(table) -> set:

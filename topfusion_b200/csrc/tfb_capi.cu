@@ -32,7 +32,7 @@ void free_all(tfb_ctx* c) {
     cudaFree(c->table); cudaFree(c->vba); cudaFree(c->vba_free); cudaFree(c->excess_free);
     cudaFree(c->claim_key); cudaFree(c->claimed); cudaFree(c->vis_type); cudaFree(c->vis_list[0]); cudaFree(c->vis_list[1]);
     cudaFree(c->minmax); cudaFree(c->raycast); cudaFree(c->dists); cudaFree(c->depth_in); cudaFree(c->icp_partial);
-    cudaFree(c->ds); cudaFree(c->l2_scratch);
+    cudaFree(c->ds); cudaFree(c->l2_scratch); cudaFree(c->marks); cudaFree(c->shard_dev);
     for (int l = 0; l < MAX_LEVELS; ++l) {
         cudaFree(c->lv[l].depth); cudaFree(c->lv[l].vcurr); cudaFree(c->lv[l].ncurr); cudaFree(c->lv[l].vprev); cudaFree(c->lv[l].nprev);
     }
@@ -124,34 +124,64 @@ int do_preprocess(tfb_ctx* c, const uint16_t* depth_dev, bool maps_into_model) {
 // ProjectiveICP::estimateTransform, projective_icp.cpp:169-212 — every iteration is one launch, nothing returns to the host
 int do_icp(tfb_ctx* c, bool update_pose) { return launch_icp_all(c, update_pose); }
 
-int do_frame(tfb_ctx* c, const uint16_t* depth_dev, int* ok) {
+constexpr int MARKS_CAP = 1 << 16;
+
+bool sharded(const tfb_ctx* c) { return c->p.shard_count > 1; }
+
+// stage A: everything up to and including the integration of this context's blocks
+int frame_begin(tfb_ctx* c, const uint16_t* depth_dev) {
+    if (c->frame_stage != 0) return set_err(c, TFB_ERR_STATE, "tfb_frame_begin: the previous frame was not finished (tfb_frame_end)");
     int r;
     stamp(c, ST_PRE);
     const bool first = (c->frame_counter == 0);
+    c->frame_first = first;
     if ((r = do_preprocess(c, depth_dev, first))) return r;
-    if (first) {
-        stamp(c, ST_ICP);
-        stamp(c, ST_ALLOC);
-        if ((r = launch_allocate(c, c->dists))) return r;
-        stamp(c, ST_INTEG);
-        if ((r = launch_integrate(c, c->dists))) return r;
-        stamp(c, ST_EXPECT); stamp(c, ST_RAYCAST); stamp(c, ST_PYR);
-    } else {
-        stamp(c, ST_ICP);
-        if ((r = do_icp(c, true))) return r;
-        stamp(c, ST_ALLOC);
-        if ((r = launch_allocate(c, c->dists))) return r;
-        stamp(c, ST_INTEG);
-        if ((r = launch_integrate(c, c->dists))) return r;
-        stamp(c, ST_EXPECT);
+    stamp(c, ST_ICP);
+    if (!first && (r = do_icp(c, true))) return r;
+    stamp(c, ST_ALLOC);
+    if ((r = launch_allocate(c, c->dists))) return r;
+    stamp(c, ST_INTEG);
+    if ((r = launch_integrate(c, c->dists))) return r;
+    stamp(c, ST_EXPECT);
+    c->frame_stage = 1;
+    return TFB_OK;
+}
+
+// stage B: expected depths + raycast (every voxel of the scene must be final: cross-GPU barrier before it when sharded)
+int frame_raycast(tfb_ctx* c) {
+    if (c->frame_stage != 1) return set_err(c, TFB_ERR_STATE, "tfb_frame_raycast: call tfb_frame_begin first");
+    int r;
+    if (!c->frame_first) {
         if ((r = launch_expected_depths(c))) return r;
         stamp(c, ST_RAYCAST);
-        if ((r = launch_icp_maps(c, c->lv[0].vprev, c->lv[0].nprev))) return r;
+        if (sharded(c)) {
+            if (c->attached != (1u << c->p.shard_count) - 1u)
+                return set_err(c, TFB_ERR_STATE, "sharded context: attach every rank's buffers first (tfb_shard_attach)");
+            if ((r = launch_raycast_sharded(c, false))) return r;
+        } else if ((r = launch_raycast(c, true))) return r;
+    } else {
+        stamp(c, ST_RAYCAST);
+    }
+    c->frame_stage = 2;
+    return TFB_OK;
+}
+
+// stage C: model maps for the next frame's ICP (every rank's rows must have arrived: barrier before it when sharded)
+int frame_end(tfb_ctx* c, int* ok) {
+    if (c->frame_stage != 2) return set_err(c, TFB_ERR_STATE, "tfb_frame_end: call tfb_frame_raycast first");
+    c->frame_stage = 0;
+    int r;
+    const bool first = c->frame_first;
+    if (!first) {
+        if (sharded(c) && (r = launch_apply_marks(c))) return r;
+        if ((r = launch_icp_maps(c, c->lv[0].vprev, c->lv[0].nprev, false))) return r;
         stamp(c, ST_PYR);
         for (int i = 1; i < c->levels; ++i)
             if ((r = launch_resize_points_normals(c, c->lv[i - 1].vprev, c->lv[i - 1].nprev, c->lv[i].vprev, c->lv[i].nprev,
                                                   c->lv[i - 1].w, c->lv[i - 1].h)))
                 return r;
+    } else {
+        stamp(c, ST_PYR);
     }
     stamp(c, ST_FRAME);
     if ((r = fetch_state(c))) return r;  // the one wait of the frame
@@ -184,6 +214,15 @@ int do_frame(tfb_ctx* c, const uint16_t* depth_dev, int* ok) {
     return TFB_OK;
 }
 
+int do_frame(tfb_ctx* c, const uint16_t* depth_dev, int* ok) {
+    if (sharded(c))
+        return set_err(c, TFB_ERR_STATE, "sharded context: drive the frame with tfb_frame_begin / _raycast / _end and a barrier between them");
+    int r;
+    if ((r = frame_begin(c, depth_dev))) { c->frame_stage = 0; return r; }
+    if ((r = frame_raycast(c))) { c->frame_stage = 0; return r; }
+    return frame_end(c, ok);
+}
+
 }  // namespace
 
 extern "C" {
@@ -212,7 +251,7 @@ int tfb_create(const tfb_params* p, void* stream, tfb_ctx** out) {
     if (p->cols <= 0 || p->rows <= 0 || (p->cols % 8) || (p->rows % 8)) return TFB_ERR_ARG;
     if (p->num_buckets <= 0 || (p->num_buckets & (p->num_buckets - 1))) return TFB_ERR_ARG;
     if (p->num_blocks <= 0 || p->excess_size <= 0 || p->voxel_size <= 0 || p->mu <= 0) return TFB_ERR_ARG;
-    if (p->shard_count < 1 || p->shard_rank < 0 || p->shard_rank >= p->shard_count) return TFB_ERR_ARG;
+    if (p->shard_count < 1 || p->shard_count > TFB_MAX_SHARDS || p->shard_rank < 0 || p->shard_rank >= p->shard_count) return TFB_ERR_ARG;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return TFB_ERR_CUDA;  // no CPU fallback, by design
 
@@ -263,6 +302,8 @@ int tfb_create(const tfb_params* p, void* stream, tfb_ctx** out) {
     c->icp_max_blocks = div_up(p->cols, 32) * div_up(p->rows, 8);
     ok(dmalloc(&c->icp_partial, (size_t)64 * (c->icp_max_blocks > 1024 ? c->icp_max_blocks : 1024) + 64));
     ok(cudaMalloc((void**)&c->ds, sizeof(DevState) + 64 * sizeof(float)));
+    ok(cudaMalloc((void**)&c->marks, (size_t)(2 + 2 * MARKS_CAP) * sizeof(unsigned int)));
+    ok(cudaMalloc((void**)&c->shard_dev, sizeof(ShardView)));
     ok(cudaMallocHost((void**)&c->hs, sizeof(DevState)));
     ok(cudaMallocHost((void**)&c->h_pose_stage, 64 * sizeof(float)));
     ok(cudaMallocHost((void**)&c->h_icp27, 32 * sizeof(float)));
@@ -288,6 +329,13 @@ int tfb_create(const tfb_params* p, void* stream, tfb_ctx** out) {
         for (size_t i = 0; i < n; ++i) tmp[i] = make_float2(p->view_frustum_min, p->view_frustum_max);
         cudaMemcpy(c->minmax, tmp, n * sizeof(float2), cudaMemcpyHostToDevice);
         free(tmp);
+    }
+    cudaMemsetAsync(c->marks, 0, 2 * sizeof(unsigned int), c->stream);
+    c->shard.rank = p->shard_rank; c->shard.count = p->shard_count; c->shard.marks_cap = MARKS_CAP;
+    {
+        tfb_shard_ptrs self;
+        tfb_shard_local_ptrs(c, &self);
+        tfb_shard_attach(c, p->shard_rank, &self);
     }
     int r = do_reset(c);
     if (r == TFB_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) r = TFB_ERR_CUDA;
@@ -516,6 +564,50 @@ int tfb_get_pose(const tfb_ctx* c, int time, float out16[16]) {
 }
 int tfb_num_poses(const tfb_ctx* c) { return c ? c->n_poses : 0; }
 
+// ---- sharded scene ------------------------------------------------------------------------------------------
+int tfb_shard_local_ptrs(tfb_ctx* c, tfb_shard_ptrs* out) {
+    if (!c || !out) return TFB_ERR_ARG;
+    out->table = c->table; out->vba = c->vba; out->raycast = c->raycast; out->marks = c->marks;
+    return TFB_OK;
+}
+int tfb_shard_attach(tfb_ctx* c, int rank, const tfb_shard_ptrs* peer) {
+    if (!c || !peer || rank < 0 || rank >= c->p.shard_count) return TFB_ERR_ARG;
+    if (!peer->table || !peer->vba || !peer->raycast || !peer->marks) return TFB_ERR_ARG;
+    c->shard.table[rank] = (const int4*)peer->table;
+    c->shard.vba[rank] = (const unsigned int*)peer->vba;
+    c->shard.raycast[rank] = (float4*)peer->raycast;
+    c->shard.marks[rank] = (unsigned int*)peer->marks;
+    c->attached |= 1u << rank;
+    TFB_CUDA(c, cudaStreamSynchronize(c->stream));   // a kernel may still be reading the device copy
+    TFB_CUDA(c, cudaMemcpy(c->shard_dev, &c->shard, sizeof(ShardView), cudaMemcpyHostToDevice));
+    return TFB_OK;
+}
+int tfb_ipc_export(const void* dev_ptr, unsigned char handle64[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t");
+    if (!dev_ptr || !handle64) return TFB_ERR_ARG;
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, const_cast<void*>(dev_ptr)) != cudaSuccess) { cudaGetLastError(); return TFB_ERR_CUDA; }
+    memcpy(handle64, &h, 64);
+    return TFB_OK;
+}
+int tfb_ipc_open(const unsigned char handle64[64], void** dev_ptr) {
+    if (!handle64 || !dev_ptr) return TFB_ERR_ARG;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    if (cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return TFB_ERR_CUDA; }
+    return TFB_OK;
+}
+int tfb_ipc_close(void* dev_ptr) { return cudaIpcCloseMemHandle(dev_ptr) == cudaSuccess ? TFB_OK : TFB_ERR_CUDA; }
+
+int tfb_frame_begin(tfb_ctx* c, const uint16_t* depth_dev) {
+    if (!c || !depth_dev) return TFB_ERR_ARG;
+    stamp(c, ST_UPLOAD);
+    return frame_begin(c, depth_dev);
+}
+int tfb_frame_raycast(tfb_ctx* c) { return c ? frame_raycast(c) : TFB_ERR_ARG; }
+int tfb_frame_end(tfb_ctx* c, int* ok) { return (c && ok) ? frame_end(c, ok) : TFB_ERR_ARG; }
+void* tfb_stream(tfb_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
 // ---- inspection -----------------------------------------------------------------------------------------
 int tfb_get_counters(tfb_ctx* c, long long out[8]) {
     if (!c || !out) return TFB_ERR_ARG;
@@ -641,7 +733,8 @@ static const char* const KNAMES[K_COUNT] = {
     "k_bilateral", "k_depth_pyr", "k_points_normals", "k_resize_points_normals", "k_compute_dists", "k_truncate",
     "k_icp_begin", "k_icp_iteration[L0]", "k_icp_iteration[L1]", "k_icp_iteration[L2]", "k_icp_iteration[L3]", "(unused)",
     "k_pose_set", "k_set_type3", "k_mark", "k_alloc", "k_visible_list", "k_list_flip", "k_integrate_begin", "k_integrate",
-    "k_minmax_init", "k_expected_depths", "k_raycast", "k_icp_maps", "k_reset_scene", "k_icp_all", "k_render_grey"};
+    "k_minmax_init", "k_expected_depths", "k_raycast", "k_icp_maps", "k_reset_scene", "k_icp_all", "k_render_grey",
+    "k_raycast_sharded", "k_apply_marks"};
 
 int tfb_ktiming_enable(tfb_ctx* c, int on) {
     if (!c) return TFB_ERR_ARG;

@@ -14,7 +14,7 @@ enum KernelId {
     K_BILATERAL = 0, K_DEPTH_PYR, K_POINTS_NORMALS, K_RESIZE_MAPS, K_COMPUTE_DISTS, K_TRUNCATE,
     K_ICP_BEGIN, K_ICP_L0, K_ICP_L1, K_ICP_L2, K_ICP_L3, K_POSE_UPDATE, K_POSE_SET,
     K_SET_TYPE3, K_MARK, K_ALLOC, K_VISIBLE_LIST, K_LIST_FLIP, K_INTEGRATE_BEGIN, K_INTEGRATE,
-    K_MINMAX_INIT, K_EXPECTED_DEPTHS, K_RAYCAST, K_ICP_MAPS, K_RESET_SCENE, K_ICP_ALL, K_RENDER_GREY, K_COUNT
+    K_MINMAX_INIT, K_EXPECTED_DEPTHS, K_RAYCAST, K_ICP_MAPS, K_RESET_SCENE, K_ICP_ALL, K_RENDER_GREY, K_RAYCAST_SHARDED, K_APPLY_MARKS, K_COUNT
 };
 constexpr int KT_MAX_EVENTS = 512;
 
@@ -71,6 +71,24 @@ struct DevState {
     // statistics
     unsigned long long voxel_updates;
     int pad_[2];
+};
+
+// payload owner of a block when the scene is sharded (new; the reference is single-GPU).  A different mix than
+// hashIndex so a rank does not end up with 1/n of its buckets.  oracle/tfo_oracle.cpp `owns` is the same.
+__host__ __device__ __forceinline__ int owner_rank(int bx, int by, int bz, int count) {
+    if (count <= 1) return 0;
+    unsigned h = ((unsigned)bx * 0x9E3779B1u) ^ ((unsigned)by * 0x85EBCA77u) ^ ((unsigned)bz * 0xC2B2AE3Du);
+    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12;
+    return (int)(h % (unsigned)count);
+}
+
+// what a rank needs of every rank (itself included) to cast rays through a sharded scene: kernel parameter, by value
+struct ShardView {
+    int rank, count, marks_cap, pad_;
+    const int4* table[TFB_MAX_SHARDS];
+    const unsigned int* vba[TFB_MAX_SHARDS];
+    float4* raycast[TFB_MAX_SHARDS];
+    unsigned int* marks[TFB_MAX_SHARDS];
 };
 
 struct LevelBuf {
@@ -144,6 +162,13 @@ struct tfb_ctx {
     cudaEvent_t mark_ev[8];
     void* l2_scratch;
     int l2_toggle;
+    // sharding
+    tfb::ShardView shard;
+    tfb::ShardView* shard_dev; // device copy (kernels that take it by pointer)
+    unsigned int attached;     // bit r set once rank r's buffers are attached
+    unsigned int* marks;       // incoming visibility marks: [0] count, [1] pad, then 2 words per mark
+    int frame_stage;           // 0 idle, 1 after tfb_frame_begin, 2 after tfb_frame_raycast
+    bool frame_first;
 };
 
 namespace tfb {
@@ -211,8 +236,10 @@ int launch_allocate(tfb_ctx* c, const float* dists);
 int launch_integrate(tfb_ctx* c, const float* dists);
 // vis
 int launch_expected_depths(tfb_ctx* c);
-int launch_icp_maps(tfb_ctx* c, float4* points, float4* normals);
+int launch_icp_maps(tfb_ctx* c, float4* points, float4* normals, bool do_raycast = true);
 int launch_render_grey(tfb_ctx* c, uchar4* out);
 int launch_raycast(tfb_ctx* c, bool update_visible);
+int launch_raycast_sharded(tfb_ctx* c, bool viewer);
+int launch_apply_marks(tfb_ctx* c);
 
 }  // namespace tfb
