@@ -314,6 +314,11 @@ int split_tiles(RenderTile* list, int offset, const int ul[2], const int lr[2], 
     return offset;
 }
 
+// debug only (tools/ray_stats.py): per-ray step / missing-block step / trilinear-read counts of the march
+static int* g_ray_stats = nullptr;
+static int g_ray_stats_cols = 0;
+extern "C" __attribute__((visibility("default"))) void tfo_debug_ray_stats(int* buf, int cols) { g_ray_stats = buf; g_ray_stats_cols = cols; }
+
 // VisualisationEngine_Shared.hpp:99-172 (modifyVisibleEntries = vis_type != nullptr)
 bool cast_ray(float out[4], uint8_t* vis_type, int x, int y, const Voxel* voxels, const HashEntry* table,
               const float inv_m[16], const float inv_proj[4], float one_over_voxel, float mu,
@@ -343,13 +348,16 @@ bool cast_ray(float out[4], uint8_t* vis_type, int x, int y, const Voxel* voxels
     BlockCache cache;
     float sdf = 1.0f, conf = 0.0f, step;
     int found;
+    int n_steps = 0, n_missing = 0, n_tri = 0;
     while (total < total_max) {
         sdf = read_nearest(voxels, table, p, found, cache, g);
+        ++n_steps;
         if (vis_type && found) vis_type[found - 1] = 1;
         if (!found) {
             step = BLOCK;
+            ++n_missing;
         } else {
-            if ((sdf <= 0.1f) && (sdf >= -0.5f)) sdf = read_trilinear(voxels, table, p, found, cache, g, nullptr);
+            if ((sdf <= 0.1f) && (sdf >= -0.5f)) { sdf = read_trilinear(voxels, table, p, found, cache, g, nullptr); ++n_tri; }
             if (sdf <= 0.0f) break;
             step = sdf * step_scale;
             step = (step < 1.0f) ? 1.0f : step;
@@ -367,6 +375,10 @@ bool cast_ray(float out[4], uint8_t* vis_type, int x, int y, const Voxel* voxels
         hit = true;
     } else {
         hit = false;
+    }
+    if (g_ray_stats) {
+        int* st = g_ray_stats + 3 * (x + y * g_ray_stats_cols);
+        st[0] = n_steps; st[1] = n_missing; st[2] = n_tri;
     }
     out[0] = p.x; out[1] = p.y; out[2] = p.z;
     out[3] = hit ? conf + 1.0f : 0.0f;

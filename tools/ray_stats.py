@@ -1,0 +1,30 @@
+"""CPU (oracle, test infrastructure): distribution of march lengths per ray and per 8x4 warp patch on the S1 orbit."""
+import ctypes as C, os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import tfo
+from topfusion_b200 import synth
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+depth, _, _ = synth.sequence("S1", n)
+L = tfo.Lib("port")
+o = tfo.Oracle(lib=L, corrected_mode=1)
+buf = np.zeros((480, 640, 3), np.int32)
+for i in range(n):
+    if i == n - 1:
+        L.lib.tfo_debug_ray_stats(buf.ctypes.data_as(C.c_void_p), C.c_int(640))
+    o.process_frame(depth[i])
+L.lib.tfo_debug_ray_stats(None, C.c_int(0))
+st, mi, tr = buf[..., 0], buf[..., 1], buf[..., 2]
+print("rays with >=1 step:", int((st > 0).sum()), "of", st.size)
+for name, a in (("steps", st), ("missing-block steps", mi), ("in-loop trilinear", tr)):
+    v = a[st > 0]
+    print(f"{name:22s} mean {v.mean():6.2f}  p50 {np.percentile(v,50):5.0f}  p90 {np.percentile(v,90):5.0f}  p99 {np.percentile(v,99):5.0f}  max {v.max():5d}")
+# per warp patch (8 wide x 4 high): the warp runs as long as its longest ray
+pm = st.reshape(120, 4, 80, 8).max(axis=(1, 3))
+print("per-warp max steps: mean %.1f p50 %.0f p90 %.0f p99 %.0f max %d; sum of warp-max %d vs sum of ray steps/32 %d" %
+      (pm.mean(), np.percentile(pm, 50), np.percentile(pm, 90), np.percentile(pm, 99), pm.max(), pm.sum(), st.sum() // 32))
+# per CTA (16x8)
+cm = st.reshape(60, 8, 40, 16).max(axis=(1, 3))
+print("per-CTA max steps: mean %.1f max %d" % (cm.mean(), cm.max()))
+ys, xs = np.unravel_index(np.argsort(pm.ravel())[-5:], pm.shape)
+print("longest warps at (patch y, x):", list(zip(ys.tolist(), xs.tolist())), pm[ys, xs])

@@ -13,7 +13,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtfusion_b200.so")
+LIB_PATH = os.environ.get("TFB_LIB_PATH") or os.path.join(_HERE, "libtfusion_b200.so")   # TFB_LIB_PATH: instrumented build (tools/)
 
 HASH_DTYPE = np.dtype([("pos", np.int16, 3), ("pad", np.int16), ("offset", np.int32), ("ptr", np.int32)])
 VOXEL_DTYPE = np.dtype([("sdf", np.int16), ("w", np.uint8), ("pad", np.uint8)])

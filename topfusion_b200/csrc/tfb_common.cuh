@@ -121,6 +121,7 @@ struct tfb_ctx {
     // allocation scratch
     unsigned int* claim_key;   // per slot, 0 = unclaimed
     int* claimed;              // compact list of claimed slots
+    unsigned int* bucket_bits; // 1 bit per bucket: head entry allocated (empty-space skipping without touching the table)
     // render state
     int* vis_type;             // per slot (reference: uchar entriesVisibleType)
     int* vis_list[2];          // double-buffered visibleEntryIDs; DevState::cur_list says which is current
