@@ -28,3 +28,10 @@ cm = st.reshape(60, 8, 40, 16).max(axis=(1, 3))
 print("per-CTA max steps: mean %.1f max %d" % (cm.mean(), cm.max()))
 ys, xs = np.unravel_index(np.argsort(pm.ravel())[-5:], pm.shape)
 print("longest warps at (patch y, x):", list(zip(ys.tolist(), xs.tolist())), pm[ys, xs])
+# the warps the GPU profile found slowest (tools/ray_profile.py on the same frame): per-lane step / missing / trilinear counts
+for w in [int(a) for a in sys.argv[2:]]:
+    cta, wi = w // 4, w % 4
+    x0, y0 = (cta % 40) * 16 + (wi & 1) * 8, (cta // 40) * 8 + (wi >> 1) * 4
+    print(f"warp {w}: pixels x {x0}..{x0+7}, y {y0}..{y0+3}")
+    for yy in range(y0, y0 + 4):
+        print("   ", " ".join(f"{st[yy,xx]:2d}/{mi[yy,xx]:2d}/{tr[yy,xx]}" for xx in range(x0, x0 + 8)))
