@@ -164,7 +164,8 @@ __device__ __forceinline__ void ldl6_f32(const float (&A)[36], Ldl6& f) {
     }
 }
 
-__device__ __forceinline__ void ldl6_solve(const Ldl6& f, const double (&r)[6], float (&x)[6]) {
+template <typename T>
+__device__ __forceinline__ void ldl6_solve(const Ldl6& f, const T (&r)[6], float (&x)[6]) {
     float y[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
@@ -182,32 +183,27 @@ __device__ __forceinline__ void ldl6_solve(const Ldl6& f, const double (&r)[6], 
     }
 }
 
-__device__ __forceinline__ bool solve6_refine(const float (&A)[36], const float (&b)[6], const Ldl6& f, double (&x)[6]) {
-    double r[6];
-    float dx[6];
+// One solve plus one step of fixed-precision refinement, everything in fp32: the accuracy class of the reference's own
+// fp32 Jacobi SVD (cv::solve(DECOMP_SVD) on Matx66f), error ~ cond(A) * 6e-8 of an increment that itself shrinks from
+// iteration to iteration.  (An earlier version refined with fp64 residuals; it was more exact than the reference and cost
+// 2.2 us of single-thread latency in each of the 19 iterations of a frame.)  Returns false when the correction does not
+// contract, which sends the system to the reference path below.
+__device__ __forceinline__ bool solve6_refine(const float (&A)[36], const float (&b)[6], const Ldl6& f, float (&x)[6]) {
+    ldl6_solve(f, b, x);
+    float r[6];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) { x[i] = 0.0; r[i] = b[i]; }
-    double first = 0.0, last = 0.0;
+    for (int i = 0; i < 6; ++i) {
+        float sacc = b[i];
 #pragma unroll
-    for (int step = 0; step < 3; ++step) {
-        ldl6_solve(f, r, dx);
-        double nrm = 0.0;
-#pragma unroll
-        for (int i = 0; i < 6; ++i) { x[i] += (double)dx[i]; nrm = fmax(nrm, fabs((double)dx[i])); }
-        if (step == 0) first = nrm;
-        last = nrm;
-        if (step < 2) {
-#pragma unroll
-            for (int i = 0; i < 6; ++i) {
-                double sacc = b[i];
-#pragma unroll
-                for (int j = 0; j < 6; ++j) sacc -= (double)A[i * 6 + j] * x[j];
-                r[i] = sacc;
-            }
-        }
+        for (int j = 0; j < 6; ++j) sacc = __fmaf_rn(-A[i * 6 + j], x[j], sacc);
+        r[i] = sacc;
     }
-    // the third correction must be at the 1e-6 level of the first (two contractions by <= 1e-3 each)
-    return (last <= first * 1e-6) || (first == 0.0);
+    float dx[6];
+    ldl6_solve(f, r, dx);
+    float nx = 0.f, nd = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { nx = fmaxf(nx, fabsf(x[i])); nd = fmaxf(nd, fabsf(dx[i])); x[i] += dx[i]; }
+    return nd <= 0.05f * nx || nx == 0.f;
 }
 
 // the reference's exact path, used when the fast path declines: cv::determinant's pivoted fp32 LU for the nullspace
@@ -224,20 +220,6 @@ __device__ __noinline__ bool solve6_reference_path(const float* Af_, const float
     for (int i = 0; i < 6; ++i) b[i] = bf_[i];
     solve6_jacobi(A, b, r_out);
     return true;
-}
-
-// sin / cos of a small angle in fp64 by series (|theta| < 0.5: truncation < 1e-17 relative); ICP increments
-// are fractions of a degree.  The generic sincos() is only used for large angles.
-__device__ __forceinline__ void sincos_small(double t, double& s, double& c) {
-    if (t < 0.5) {
-        const double t2 = t * t;
-        s = t * (1.0 + t2 * (-1.0 / 6 + t2 * (1.0 / 120 + t2 * (-1.0 / 5040 + t2 * (1.0 / 362880 + t2 * (-1.0 / 39916800 +
-                 t2 * (1.0 / 6227020800.0 + t2 * (-1.0 / 1307674368000.0))))))));
-        c = 1.0 + t2 * (-0.5 + t2 * (1.0 / 24 + t2 * (-1.0 / 720 + t2 * (1.0 / 40320 + t2 * (-1.0 / 3628800 +
-                 t2 * (1.0 / 479001600.0 + t2 * (-1.0 / 87178291200.0 + t2 * (1.0 / 20922789888000.0))))))));
-    } else {
-        sincos(t, &s, &c);
-    }
 }
 
 // StreamHelper::get unpack (projective_icp.cpp:43-62), nullspace test (:197-203), solve (:206),
@@ -259,34 +241,39 @@ __device__ __noinline__ bool icp_solve_update(const double* v27, float* aff_io) 
                 else { Af[j * 6 + i] = value; Af[i * 6 + j] = value; }
             }
     }
-    double r[6];
+    float rf[6];
     Ldl6 f;
     ldl6_f32(Af, f);
     bool solved = false;
-    if (f.ok && f.det == f.det && fabs(f.det) >= 1e-15) solved = solve6_refine(Af, bf, f, r);
-    if (!solved && !solve6_reference_path(Af, bf, r)) return false;
-    float rf[6];
+    if (f.ok && f.det == f.det && fabs(f.det) >= 1e-15) solved = solve6_refine(Af, bf, f, rf);
+    if (!solved) {
+        double r[6];
+        if (!solve6_reference_path(Af, bf, r)) return false;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) rf[i] = (float)r[i];
+        for (int i = 0; i < 6; ++i) rf[i] = (float)r[i];
+    }
 
-    // cv::Affine3f(rvec, t): Rodrigues evaluated in double, stored as float
+    // cv::Affine3f(rvec, t) = Rodrigues: R = cos I + (1 - cos) r r^T + sin [r]x.  OpenCV evaluates it
+    // in double and stores float; the increments here are fractions of a degree, where fp32 series for sin, cos and
+    // (1 - cos) — the latter summed directly, without the cancellation of 1 - cos — are exact to the last float bit or two.
     float T[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
-    const double theta = sqrt((double)rf[0] * rf[0] + (double)rf[1] * rf[1] + (double)rf[2] * rf[2]);
-    if (theta >= 2.220446049250313e-16) {
-        double sn, cs;
-        sincos_small(theta, sn, cs);
-        const double c1 = 1. - cs, it = 1. / theta;
-        const float rx = (float)(rf[0] * it), ry = (float)(rf[1] * it), rz = (float)(rf[2] * it);
-        const double rrt[9] = {(double)rx * rx, (double)rx * ry, (double)rx * rz, (double)rx * ry, (double)ry * ry,
-                               (double)ry * rz, (double)rx * rz, (double)ry * rz, (double)rz * rz};
-        const double rc[9] = {0, -(double)rz, (double)ry, (double)rz, 0, -(double)rx, -(double)ry, (double)rx, 0};
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const int k = i * 3 + j;
-                T[i * 4 + j] = (float)(cs * (i == j ? 1.0 : 0.0) + c1 * rrt[k] + sn * rc[k]);
-            }
+    const float t2 = rf[0] * rf[0] + rf[1] * rf[1] + rf[2] * rf[2];
+    if (t2 > 0.f) {
+        const float theta = sqrtf(t2);
+        float sn, cs, c1;
+        if (theta < 0.5f) {
+            sn = theta * (1.0f + t2 * (-1.0f / 6 + t2 * (1.0f / 120 + t2 * (-1.0f / 5040 + t2 * (1.0f / 362880)))));
+            c1 = t2 * (0.5f + t2 * (-1.0f / 24 + t2 * (1.0f / 720 + t2 * (-1.0f / 40320 + t2 * (1.0f / 3628800)))));
+            cs = 1.0f - c1;
+        } else {
+            sincosf(theta, &sn, &cs);
+            c1 = 1.0f - cs;
+        }
+        const float it = 1.0f / theta;
+        const float rx = rf[0] * it, ry = rf[1] * it, rz = rf[2] * it;
+        T[0] = cs + c1 * rx * rx;      T[1] = c1 * rx * ry - sn * rz; T[2] = c1 * rx * rz + sn * ry;
+        T[4] = c1 * rx * ry + sn * rz; T[5] = cs + c1 * ry * ry;      T[6] = c1 * ry * rz - sn * rx;
+        T[8] = c1 * rx * rz - sn * ry; T[9] = c1 * ry * rz + sn * rx; T[10] = cs + c1 * rz * rz;
     }
     T[3] = rf[3]; T[7] = rf[4]; T[11] = rf[5];
     float nw[16];
@@ -459,17 +446,30 @@ struct IcpAllArgs {
     int update_pose;
 };
 
-constexpr int ICPA_THREADS = 512, ICPA_WARPS = ICPA_THREADS / 32, ICPA_UNROLL = 4;   // one CTA per SM
+constexpr int ICPA_THREADS = 512, ICPA_WARPS = ICPA_THREADS / 32, ICPA_UNROLL = 5;   // one CTA per SM
 
+// Grid barrier of the co-resident (cooperatively launched) CTAs.  Arrival is one release-reduction: it orders the CTA's
+// partial row (made visible to thread 0 by the bar.sync before it) ahead of the count.  The wait polls with relaxed
+// loads and deliberately issues NO acquire fence: on sm_100a an acquire (like __threadfence) is MEMBAR + CCTL.IVALL, which
+// throws away the SM's L1 — and with it the vertex / normal maps this CTA re-reads in every one of the 10/5/4 iterations
+// of a level.  Nothing read after the barrier can be stale in L1: the partial rows are read with L2-scope loads
+// (ld.relaxed.gpu), the maps are read-only for the whole kernel, the transform lives in shared memory.
 __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(counter, 1u);
-        while (*((volatile unsigned int*)counter) < target) { }
-        __threadfence();
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+        unsigned int v;
+        do {
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        } while (v < target);
     }
     __syncthreads();
+}
+
+__device__ __forceinline__ float ld_partial(const float* p) {
+    float v;
+    asm volatile("ld.relaxed.gpu.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
 }
 
 #ifdef TFB_ICP_PROFILE
@@ -566,13 +566,24 @@ __global__ void __launch_bounds__(ICPA_THREADS, 1)
             }
 
             ICP_STAMP(1);
-            // CTA reduction -> one row of partials
+            // CTA reduction -> one row of partials.  Warp level: a transposing butterfly — at each of the five steps a lane
+            // keeps one half of its values and trades the other half with its partner, so the 28 sums cost 31 shuffles
+            // instead of 28 x 5, and lane L ends up holding the warp total of term L.
+            {
+                float v[32];
 #pragma unroll
-            for (int i = 0; i < ICP_ACC; ++i) {
-                float vsum = acc[i];
+                for (int i = 0; i < 32; ++i) v[i] = (i < ICP_ACC) ? acc[i] : 0.f;
 #pragma unroll
-                for (int o = 16; o >= 1; o >>= 1) vsum += __shfl_xor_sync(0xffffffffu, vsum, o);
-                if (lane == 0) s_warp[warp][i] = vsum;
+                for (int o = 16; o >= 1; o >>= 1) {
+                    const bool upper = (lane & o) != 0;
+#pragma unroll
+                    for (int i = 0; i < o; ++i) {
+                        const float send = upper ? v[i] : v[i + o];
+                        const float keep = upper ? v[i + o] : v[i];
+                        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                    }
+                }
+                if (lane < ICP_ACC) s_warp[warp][lane] = v[0];
             }
             __syncthreads();
             float* prow = partial + (size_t)(iter_global & 1) * nblk * 32;
@@ -599,7 +610,7 @@ __global__ void __launch_bounds__(ICPA_THREADS, 1)
 #pragma unroll
                     for (int j = 0; j < 10; ++j) {
                         const int b = b0 + j * ICPA_WARPS;
-                        tmp[j] = (b < nblk) ? __ldcg(prow + b * 32 + k) : 0.f;
+                        tmp[j] = (b < nblk) ? ld_partial(prow + b * 32 + k) : 0.f;
                     }
 #pragma unroll
                     for (int j = 0; j < 10; ++j) sd += (double)tmp[j];
