@@ -479,6 +479,70 @@ __device__ long long g_icp_prof[64 * 8];
 #define ICP_STAMP(slot) do { } while (0)
 #endif
 
+// Pixel phase of one iteration: U independent pixels in flight per thread so the dependent chain own pixel -> projection ->
+// gathered model pixel overlaps across pixels (find_coresp + the row of icp_helper_kernel, proj_icp.cu:80-117,369-376).
+template <int U>
+__device__ __forceinline__ void icp_pixels(const IcpLevelArgs& L, const IcpAllArgs& a, int npx, int gtid, int gstride,
+                                           const float* __restrict__ s_aff, float (&acc)[ICP_ACC]) {
+    const float r00 = s_aff[0], r01 = s_aff[1], r02 = s_aff[2], t0 = s_aff[3];
+    const float r10 = s_aff[4], r11 = s_aff[5], r12 = s_aff[6], t1 = s_aff[7];
+    const float r20 = s_aff[8], r21 = s_aff[9], r22 = s_aff[10], t2 = s_aff[11];
+    for (int base = gtid; base < npx; base += gstride * U) {
+        // stage 1: own pixel loads for U independent pixels
+        float4 v[U], nc[U];
+        int idx[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            idx[u] = base + u * gstride;
+            const bool in = idx[u] < npx;
+            const float qn = __int_as_float(0x7fffffff);
+            v[u] = in ? __ldg(L.vcurr + idx[u]) : make_float4(qn, qn, qn, qn);
+            nc[u] = in ? __ldg(L.ncurr + idx[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        // stage 2: project, issue the gathers
+        float sx[U], sy[U], sz[U];
+        float4 d[U], nd[U];
+        bool valid[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            // find_coresp, proj_icp.cu:80-117 (points variant)
+            sx[u] = dot3(r00, r01, r02, v[u].x, v[u].y, v[u].z) + t0;
+            sy[u] = dot3(r10, r11, r12, v[u].x, v[u].y, v[u].z) + t1;
+            sz[u] = dot3(r20, r21, r22, v[u].x, v[u].y, v[u].z) + t2;
+            const float cox = __fmaf_rn(L.fx, __fdiv_rn(sx[u], sz[u]), L.cx);
+            const float coy = __fmaf_rn(L.fy, __fdiv_rn(sy[u], sz[u]), L.cy);
+            valid[u] = !isnan(v[u].x) && !(sz[u] <= 0 || cox < 0 || coy < 0 || cox >= L.w || coy >= L.h);
+            const int pidx = valid[u] ? ((int)coy * L.w + (int)cox) : 0;   // point-sampled texel
+            d[u] = __ldg(L.vprev + pidx);
+            nd[u] = __ldg(L.nprev + pidx);
+        }
+        // stage 3: tests + accumulation
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (!valid[u] || isnan(d[u].x)) continue;
+            const float ex = sx[u] - d[u].x, ey = sy[u] - d[u].y, ez = sz[u] - d[u].z;
+            if (dot3(ex, ey, ez, ex, ey, ez) > a.dist2_thres) continue;
+            const float nsx = dot3(r00, r01, r02, nc[u].x, nc[u].y, nc[u].z);
+            const float nsy = dot3(r10, r11, r12, nc[u].x, nc[u].y, nc[u].z);
+            const float nsz = dot3(r20, r21, r22, nc[u].x, nc[u].y, nc[u].z);
+            if (fabsf(dot3(nsx, nsy, nsz, nd[u].x, nd[u].y, nd[u].z)) < a.min_cosine) continue;
+            float row[7];
+            row[0] = sy[u] * nd[u].z - sz[u] * nd[u].y;
+            row[1] = sz[u] * nd[u].x - sx[u] * nd[u].z;
+            row[2] = sx[u] * nd[u].y - sy[u] * nd[u].x;
+            row[3] = nd[u].x; row[4] = nd[u].y; row[5] = nd[u].z;
+            row[6] = dot3(nd[u].x, nd[u].y, nd[u].z, d[u].x - sx[u], d[u].y - sy[u], d[u].z - sz[u]);
+            int k = 0;
+#pragma unroll
+            for (int i = 0; i < 6; ++i)
+#pragma unroll
+                for (int j = i; j < 7; ++j) { acc[k] = __fmaf_rn(row[i], row[j], acc[k]); ++k; }
+            acc[ICP_TERMS] += 1.f;
+        }
+    }
+
+}
+
 __global__ void __launch_bounds__(ICPA_THREADS, 1)
     k_icp_all(IcpAllArgs a, DevState* __restrict__ ds, float* __restrict__ partial, unsigned int* __restrict__ barrier) {
     __shared__ float s_warp[ICPA_WARPS][ICP_ACC];
@@ -503,67 +567,16 @@ __global__ void __launch_bounds__(ICPA_THREADS, 1)
         const IcpLevelArgs L = a.lv[l];
         const int npx = L.w * L.h;
         for (int it = 0; it < L.iters && ok; ++it, ++iter_global) {
-            const float r00 = s_aff[0], r01 = s_aff[1], r02 = s_aff[2], t0 = s_aff[3];
-            const float r10 = s_aff[4], r11 = s_aff[5], r12 = s_aff[6], t1 = s_aff[7];
-            const float r20 = s_aff[8], r21 = s_aff[9], r22 = s_aff[10], t2 = s_aff[11];
             float acc[ICP_ACC];
 #pragma unroll
             for (int i = 0; i < ICP_ACC; ++i) acc[i] = 0.f;
             ICP_STAMP(0);
 
-            for (int base = gtid; base < npx; base += gstride * ICPA_UNROLL) {
-                // stage 1: own pixel loads for ICPA_UNROLL independent pixels
-                float4 v[ICPA_UNROLL], nc[ICPA_UNROLL];
-                int idx[ICPA_UNROLL];
-#pragma unroll
-                for (int u = 0; u < ICPA_UNROLL; ++u) {
-                    idx[u] = base + u * gstride;
-                    const bool in = idx[u] < npx;
-                    const float qn = __int_as_float(0x7fffffff);
-                    v[u] = in ? __ldg(L.vcurr + idx[u]) : make_float4(qn, qn, qn, qn);
-                    nc[u] = in ? __ldg(L.ncurr + idx[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                // stage 2: project, issue the gathers
-                float sx[ICPA_UNROLL], sy[ICPA_UNROLL], sz[ICPA_UNROLL];
-                float4 d[ICPA_UNROLL], nd[ICPA_UNROLL];
-                bool valid[ICPA_UNROLL];
-#pragma unroll
-                for (int u = 0; u < ICPA_UNROLL; ++u) {
-                    // find_coresp, proj_icp.cu:80-117 (points variant)
-                    sx[u] = dot3(r00, r01, r02, v[u].x, v[u].y, v[u].z) + t0;
-                    sy[u] = dot3(r10, r11, r12, v[u].x, v[u].y, v[u].z) + t1;
-                    sz[u] = dot3(r20, r21, r22, v[u].x, v[u].y, v[u].z) + t2;
-                    const float cox = __fmaf_rn(L.fx, __fdiv_rn(sx[u], sz[u]), L.cx);
-                    const float coy = __fmaf_rn(L.fy, __fdiv_rn(sy[u], sz[u]), L.cy);
-                    valid[u] = !isnan(v[u].x) && !(sz[u] <= 0 || cox < 0 || coy < 0 || cox >= L.w || coy >= L.h);
-                    const int pidx = valid[u] ? ((int)coy * L.w + (int)cox) : 0;   // point-sampled texel
-                    d[u] = __ldg(L.vprev + pidx);
-                    nd[u] = __ldg(L.nprev + pidx);
-                }
-                // stage 3: tests + accumulation
-#pragma unroll
-                for (int u = 0; u < ICPA_UNROLL; ++u) {
-                    if (!valid[u] || isnan(d[u].x)) continue;
-                    const float ex = sx[u] - d[u].x, ey = sy[u] - d[u].y, ez = sz[u] - d[u].z;
-                    if (dot3(ex, ey, ez, ex, ey, ez) > a.dist2_thres) continue;
-                    const float nsx = dot3(r00, r01, r02, nc[u].x, nc[u].y, nc[u].z);
-                    const float nsy = dot3(r10, r11, r12, nc[u].x, nc[u].y, nc[u].z);
-                    const float nsz = dot3(r20, r21, r22, nc[u].x, nc[u].y, nc[u].z);
-                    if (fabsf(dot3(nsx, nsy, nsz, nd[u].x, nd[u].y, nd[u].z)) < a.min_cosine) continue;
-                    float row[7];
-                    row[0] = sy[u] * nd[u].z - sz[u] * nd[u].y;
-                    row[1] = sz[u] * nd[u].x - sx[u] * nd[u].z;
-                    row[2] = sx[u] * nd[u].y - sy[u] * nd[u].x;
-                    row[3] = nd[u].x; row[4] = nd[u].y; row[5] = nd[u].z;
-                    row[6] = dot3(nd[u].x, nd[u].y, nd[u].z, d[u].x - sx[u], d[u].y - sy[u], d[u].z - sz[u]);
-                    int k = 0;
-#pragma unroll
-                    for (int i = 0; i < 6; ++i)
-#pragma unroll
-                        for (int j = i; j < 7; ++j) acc[k++] += row[i] * row[j];
-                    acc[ICP_TERMS] += 1.f;
-                }
-            }
+            // pixels in flight per thread sized to the level: 5 at 640x480 (4.05 pixels per thread), 2 and 1 on the coarse levels
+            const int per_thread = (npx + gstride - 1) / gstride;
+            if (per_thread <= 1) icp_pixels<1>(L, a, npx, gtid, gstride, s_aff, acc);
+            else if (per_thread <= 2) icp_pixels<2>(L, a, npx, gtid, gstride, s_aff, acc);
+            else icp_pixels<ICPA_UNROLL>(L, a, npx, gtid, gstride, s_aff, acc);
 
             ICP_STAMP(1);
             // CTA reduction -> one row of partials.  Warp level: a transposing butterfly — at each of the five steps a lane
