@@ -151,7 +151,7 @@ def test_gpu_launch_counter_and_timing(gpu, s1_frames):
         n0 = g.kernel_launches()
         for i in range(3):
             assert g.process_frame(depth[i])
-        assert g.kernel_launches() - n0 > 40
+        assert g.kernel_launches() - n0 >= 30   # 8 on the first frame, 14 per frame afterwards
         ms = g.stage_ms()
         assert ms["frame"] > 0 and ms["icp"] > 0 and ms["integrate"] > 0
     finally:

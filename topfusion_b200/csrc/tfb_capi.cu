@@ -106,16 +106,16 @@ int do_preprocess(tfb_ctx* c, const uint16_t* depth_dev, bool maps_into_model) {
     int r = launch_bilateral(c, depth_dev, c->lv[0].depth, p.cols, p.rows, p.bilateral_kernel_size, p.bilateral_sigma_spatial,
                              p.bilateral_sigma_depth, p.icp_truncate_depth_dist, c->dists);
     if (r) return r;
-    for (int i = 1; i < c->levels; ++i) {
-        r = launch_depth_pyr(c, c->lv[i - 1].depth, c->lv[i].depth, c->lv[i - 1].w, c->lv[i - 1].h, p.bilateral_sigma_depth);
-        if (r) return r;
-    }
     for (int i = 0; i < c->levels; ++i) {
         int div = 1 << i;  // Intr::operator()(level), src/precomp.cpp:10-14
         // frame 0 ends with curr_.points_pyr.swap(prev_.points_pyr) (topfu.cpp:205-207): write the model maps directly
         float4* v = maps_into_model ? c->lv[i].vprev : c->lv[i].vcurr;
         float4* n = maps_into_model ? c->lv[i].nprev : c->lv[i].ncurr;
-        r = launch_points_normals(c, c->lv[i].depth, v, n, c->lv[i].w, c->lv[i].h, p.fx / div, p.fy / div, p.cx / div, p.cy / div);
+        if (i + 1 < c->levels)   // level i -> depth of level i+1 and maps of level i, one launch
+            r = launch_pyr_maps(c, c->lv[i].depth, c->lv[i + 1].depth, v, n, c->lv[i].w, c->lv[i].h, p.bilateral_sigma_depth, p.fx / div,
+                                p.fy / div, p.cx / div, p.cy / div);
+        else
+            r = launch_points_normals(c, c->lv[i].depth, v, n, c->lv[i].w, c->lv[i].h, p.fx / div, p.fy / div, p.cx / div, p.cy / div);
         if (r) return r;
     }
     return TFB_OK;
@@ -174,12 +174,8 @@ int frame_end(tfb_ctx* c, int* ok) {
     const bool first = c->frame_first;
     if (!first) {
         if (sharded(c) && (r = launch_apply_marks(c))) return r;
-        if ((r = launch_icp_maps(c, c->lv[0].vprev, c->lv[0].nprev, false))) return r;
+        if ((r = launch_model_maps(c))) return r;
         stamp(c, ST_PYR);
-        for (int i = 1; i < c->levels; ++i)
-            if ((r = launch_resize_points_normals(c, c->lv[i - 1].vprev, c->lv[i - 1].nprev, c->lv[i].vprev, c->lv[i].nprev,
-                                                  c->lv[i - 1].w, c->lv[i - 1].h)))
-                return r;
     } else {
         stamp(c, ST_PYR);
     }
@@ -457,6 +453,7 @@ int tfb_integrate_into_scene(tfb_ctx* c, const float pose_w2c[16], const float* 
     if (!c || !pose_w2c || !dists_dev) return TFB_ERR_ARG;
     int r = launch_pose_set(c, pose_w2c, true);
     if (r) return r;
+    TFB_CUDA(c, cudaMemsetAsync(&c->ds->voxel_updates, 0, sizeof(unsigned long long), c->stream));
     r = launch_integrate(c, dists_dev);
     if (r) return r;
     if ((r = fetch_state(c))) return r;
@@ -467,7 +464,7 @@ int tfb_create_expected_depths(tfb_ctx* c, const float pose_w2c[16]) {
     if (!c || !pose_w2c) return TFB_ERR_ARG;
     int r = launch_pose_set(c, pose_w2c, true);
     if (r) return r;
-    return launch_expected_depths(c);
+    return launch_expected_depths(c, true);
 }
 int tfb_create_icp_maps(tfb_ctx* c, const float pose_c2w[16], float* points_dev, float* normals_dev) {
     if (!c || !pose_c2w || !points_dev || !normals_dev) return TFB_ERR_ARG;
@@ -735,7 +732,7 @@ static const char* const KNAMES[K_COUNT] = {
     "k_icp_begin", "k_icp_iteration[L0]", "k_icp_iteration[L1]", "k_icp_iteration[L2]", "k_icp_iteration[L3]", "(unused)",
     "k_pose_set", "k_set_type3", "k_mark", "k_alloc", "k_visible_list", "k_list_flip", "k_integrate_begin", "k_integrate",
     "k_minmax_init", "k_expected_depths", "k_raycast", "k_icp_maps", "k_reset_scene", "k_icp_all", "k_render_grey",
-    "k_raycast_sharded", "k_apply_marks"};
+    "k_raycast_sharded", "k_apply_marks", "k_model_maps", "k_pyramid_maps"};
 
 int tfb_ktiming_enable(tfb_ctx* c, int on) {
     if (!c) return TFB_ERR_ARG;

@@ -14,7 +14,7 @@ enum KernelId {
     K_BILATERAL = 0, K_DEPTH_PYR, K_POINTS_NORMALS, K_RESIZE_MAPS, K_COMPUTE_DISTS, K_TRUNCATE,
     K_ICP_BEGIN, K_ICP_L0, K_ICP_L1, K_ICP_L2, K_ICP_L3, K_POSE_UPDATE, K_POSE_SET,
     K_SET_TYPE3, K_MARK, K_ALLOC, K_VISIBLE_LIST, K_LIST_FLIP, K_INTEGRATE_BEGIN, K_INTEGRATE,
-    K_MINMAX_INIT, K_EXPECTED_DEPTHS, K_RAYCAST, K_ICP_MAPS, K_RESET_SCENE, K_ICP_ALL, K_RENDER_GREY, K_RAYCAST_SHARDED, K_APPLY_MARKS, K_COUNT
+    K_MINMAX_INIT, K_EXPECTED_DEPTHS, K_RAYCAST, K_ICP_MAPS, K_RESET_SCENE, K_ICP_ALL, K_RENDER_GREY, K_RAYCAST_SHARDED, K_APPLY_MARKS, K_MODEL_MAPS, K_PYR_MAPS, K_COUNT
 };
 constexpr int KT_MAX_EVENTS = 512;
 
@@ -70,7 +70,8 @@ struct DevState {
     int icp_corresp;
     // statistics
     unsigned long long voxel_updates;
-    int pad_[2];
+    unsigned int list_ticket;   // CTAs of k_visible_list that are done; the last one flips the lists
+    int pad_[1];
 };
 
 // payload owner of a block when the scene is sharded (new; the reference is single-GPU).  A different mix than
@@ -219,6 +220,8 @@ int launch_bilateral(tfb_ctx* c, const uint16_t* src, uint16_t* dst, int w, int 
                      float trunc_m, float* dists_or_null);
 int launch_truncate(tfb_ctx* c, uint16_t* depth, int w, int h, float max_dist);
 int launch_depth_pyr(tfb_ctx* c, const uint16_t* src, uint16_t* dst, int sw, int sh, float sigma_depth_m);
+int launch_pyr_maps(tfb_ctx* c, const uint16_t* src, uint16_t* dst, float4* pts, float4* nrm, int sw, int sh, float sigma_depth_m,
+                    float fx, float fy, float cx, float cy);
 int launch_points_normals(tfb_ctx* c, const uint16_t* depth, float4* pts, float4* nrm, int w, int h, float fx, float fy,
                           float cx, float cy);
 int launch_resize_points_normals(tfb_ctx* c, const float4* v, const float4* n, float4* vo, float4* no, int sw, int sh);
@@ -236,11 +239,12 @@ int launch_reset_scene(tfb_ctx* c);
 int launch_allocate(tfb_ctx* c, const float* dists);
 int launch_integrate(tfb_ctx* c, const float* dists);
 // vis
-int launch_expected_depths(tfb_ctx* c);
+int launch_expected_depths(tfb_ctx* c, bool reset_image = false);
 int launch_icp_maps(tfb_ctx* c, float4* points, float4* normals, bool do_raycast = true);
 int launch_render_grey(tfb_ctx* c, uchar4* out);
 int launch_raycast(tfb_ctx* c, bool update_visible);
 int launch_raycast_sharded(tfb_ctx* c, bool viewer);
 int launch_apply_marks(tfb_ctx* c);
+int launch_model_maps(tfb_ctx* c);
 
 }  // namespace tfb

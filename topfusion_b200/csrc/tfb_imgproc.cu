@@ -183,6 +183,79 @@ __global__ void __launch_bounds__(256) k_points_normals(const uint16_t* __restri
     normals[y * w + x] = n;
 }
 
+// One launch per pyramid level in the frame path: the CTA stages a (64+4) x (16+4) tile of level l once and produces from it
+// both the 32 x 8 tile of level l+1 (pyramid_kernel, imgproc.cu:98-127) and the vertex / normal maps of its 64 x 16 pixels of
+// level l (points_normals_kernel, imgproc.cu:214-243) — the reference reads level l twice, in two kernels.
+__global__ void __launch_bounds__(PY_TX* PY_TY)
+    k_pyr_maps(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, float4* __restrict__ points, float4* __restrict__ normals,
+               int sw, int sh, int dw, int dh, float thr, float finvx, float finvy, float cx, float cy) {
+    constexpr int TW = 2 * PY_TX + 4, TH = 2 * PY_TY + 4;
+    __shared__ uint16_t tile[TH][TW];
+    const int x0 = 2 * blockIdx.x * PY_TX - 2, y0 = 2 * blockIdx.y * PY_TY - 2;
+    const int tid = threadIdx.y * PY_TX + threadIdx.x;
+    for (int i = tid; i < TW * TH; i += PY_TX * PY_TY) {
+        int tx = i % TW, ty = i / TW;
+        int gx = x0 + tx, gy = y0 + ty;
+        tile[ty][tx] = (gx >= 0 && gx < sw && gy >= 0 && gy < sh) ? src[gy * sw + gx] : (uint16_t)0;
+    }
+    __syncthreads();
+    // level l + 1
+    {
+        const int x = blockIdx.x * PY_TX + threadIdx.x, y = blockIdx.y * PY_TY + threadIdx.y;
+        if (x < dw && y < dh) {
+            const int D = 5;
+            const int center = tile[2 * y - y0][2 * x - x0];
+            const int txe = min(2 * x - D / 2 + D, sw - 1), tye = min(2 * y - D / 2 + D, sh - 1);
+            int sum = 0, count = 0;
+            for (int cy2 = max(0, 2 * y - D / 2); cy2 < tye; ++cy2)
+                for (int cx2 = max(0, 2 * x - D / 2); cx2 < txe; ++cx2) {
+                    int val = tile[cy2 - y0][cx2 - x0];
+                    if (abs(val - center) < thr) { sum += val; ++count; }
+                }
+            dst[y * dw + x] = (uint16_t)((count == 0) ? 0 : sum / count);
+        }
+    }
+    // maps of level l: 64 x 16 pixels, four per thread, a row of 64 per two warps (coalesced 16 B stores)
+    const float qnan = __int_as_float(0x7fffffff);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = tid + k * PY_TX * PY_TY;
+        const int lx = i & (2 * PY_TX - 1), ly = i / (2 * PY_TX);
+        const int x = 2 * blockIdx.x * PY_TX + lx, y = 2 * blockIdx.y * PY_TY + ly;
+        if (x >= sw || y >= sh) continue;
+        float4 p = make_float4(qnan, qnan, qnan, qnan), n = p;
+        if (x < sw - 1 && y < sh - 1) {
+            float z00 = tile[ly + 2][lx + 2] * 0.001f;
+            float z01 = tile[ly + 2][lx + 3] * 0.001f;
+            float z10 = tile[ly + 3][lx + 2] * 0.001f;
+            if (z00 * z01 * z10 != 0) {
+                float3 v00 = make_float3(z00 * (x - cx) * finvx, z00 * (y - cy) * finvy, z00);
+                float3 v01 = make_float3(z01 * (x + 1 - cx) * finvx, z01 * (y - cy) * finvy, z01);
+                float3 v10 = make_float3(z10 * (x - cx) * finvx, z10 * (y + 1 - cy) * finvy, z10);
+                float3 a = make_float3(v01.x - v00.x, v01.y - v00.y, v01.z - v00.z);
+                float3 b = make_float3(v10.x - v00.x, v10.y - v00.y, v10.z - v00.z);
+                float3 cr = make_float3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+                float r = 1.0f / sqrtf(__fmaf_rn(cr.x, cr.x, __fmaf_rn(cr.y, cr.y, cr.z * cr.z)));  // reference: rsqrt (approximate)
+                n = make_float4(-(cr.x * r), -(cr.y * r), -(cr.z * r), 1.0f);
+                p = make_float4(v00.x, v00.y, v00.z, 1.0f);
+            }
+        }
+        points[y * sw + x] = p;
+        normals[y * sw + x] = n;
+    }
+}
+
+int launch_pyr_maps(tfb_ctx* c, const uint16_t* src, uint16_t* dst, float4* pts, float4* nrm, int sw, int sh, float sigma_depth_m,
+                    float fx, float fy, float cx, float cy) {
+    float thr = sigma_depth_m * 1000 * 3;  // imgproc.cu:132,138
+    int dw = sw / 2, dh = sh / 2;
+    dim3 block(PY_TX, PY_TY), grid(div_up(sw, 2 * PY_TX), div_up(sh, 2 * PY_TY));
+    TFB_KT(c, K_PYR_MAPS);
+    k_pyr_maps<<<grid, block, 0, c->stream>>>(src, dst, pts, nrm, sw, sh, dw, dh, thr, 1.f / fx, 1.f / fy, cx, cy);
+    TFB_LAUNCH_CHECK(c);
+    return TFB_OK;
+}
+
 int launch_points_normals(tfb_ctx* c, const uint16_t* depth, float4* pts, float4* nrm, int w, int h, float fx, float fy, float cx,
                           float cy) {
     dim3 block(32, 8), grid(div_up(w, 32), div_up(h, 8));
