@@ -62,6 +62,10 @@ typedef struct tfb_params {
     int32_t depth_cutoff_mm;        /* src/cuda/imgproc.cu:277 hard-codes 2047 */
     int32_t corrected_mode;         /* 0: reference behaviour incl. SURVEY.md F1; 1: model maps in the camera frame */
     int32_t shard_rank, shard_count;/* voxel payload sharded by block coordinate; index replicated */
+    int32_t defer_tail;             /* 1 (default): tfb_process_frame returns as soon as the pose is known; allocation,
+                                     * integration, raycast and model maps of that frame are enqueued by the next call (beside
+                                     * its preprocessing, on a second stream) or by any call that looks at the scene.  0: the
+                                     * whole frame is finished before the call returns.  Results are identical. */
 } tfb_params;
 
 typedef struct tfb_ctx tfb_ctx;
@@ -199,7 +203,8 @@ TFB_API void* tfb_stream(tfb_ctx* c);   /* the cudaStream_t the context runs on 
 /* out[8] = n_visible, last_free_block, last_free_excess, n_new_this_frame, frame_counter, resets,
  *          n_raycast_extras, n_allocated */
 TFB_API int tfb_get_counters(tfb_ctx* c, long long out[8]);
-TFB_API long long tfb_voxel_updates_last(tfb_ctx* c);   /* 512 x visible entries with ptr >= 0 */
+TFB_API long long tfb_voxel_updates_last(tfb_ctx* c);   /* 512 x visible entries with ptr >= 0; finishes a deferred tail */
+TFB_API long long tfb_voxel_updates_total(const tfb_ctx* c);   /* summed over every integration finished so far; does not wait */
 TFB_API int tfb_total_entries(const tfb_ctx* c);
 TFB_API int tfb_export_table(tfb_ctx* c, void* host_entries);       /* total_entries x 16 B HashEntry */
 TFB_API int tfb_export_vis_type(tfb_ctx* c, uint8_t* host);         /* total_entries */
@@ -215,8 +220,9 @@ TFB_API int tfb_import_level(tfb_ctx* c, int which, int level, const void* host)
 TFB_API void* tfb_level_ptr(tfb_ctx* c, int which, int level);
 
 /* ---- timing on the context stream (CUDA events) -------------------------------------------
- * stage ids: 0 upload, 1 preprocess, 2 icp, 3 allocate, 4 integrate, 5 expected depth,
- *            6 raycast + icp maps, 7 map pyramid, 8 whole frame */
+ * stage ids: 0 upload, 1 preprocess (upload + preprocessing, on the second stream), 2 icp, 3 allocate, 4 integrate,
+ *            5 expected depth, 6 raycast + model maps, 7 wait for the preprocessing stream, 8 whole call.
+ *            With defer_tail, stages 3..6 of a call are those of the PREVIOUS frame (they run first, beside stage 1). */
 TFB_API int tfb_timing_enable(tfb_ctx* c, int on);
 TFB_API int tfb_timing_last_ms(tfb_ctx* c, float out9[9]);
 /* number of kernels this library launched since the context was created */

@@ -149,9 +149,9 @@ def test_gpu_launch_counter_and_timing(gpu, s1_frames):
     try:
         g.timing(True)
         n0 = g.kernel_launches()
-        for i in range(3):
+        for i in range(4):
             assert g.process_frame(depth[i])
-        assert g.kernel_launches() - n0 >= 30   # 8 on the first frame, 14 per frame afterwards
+        assert g.kernel_launches() - n0 >= 30   # 8 on the first frame, 14 per frame afterwards (the last tail is still pending)
         ms = g.stage_ms()
         assert ms["frame"] > 0 and ms["icp"] > 0 and ms["integrate"] > 0
     finally:
@@ -193,3 +193,28 @@ def test_against_committed_golden_vectors(gpu):
             assert len(got ^ want) <= (max(8, len(want) // 100) if cols >= 640 else len(want) // 8), (path, len(got ^ want))
         finally:
             g.close()
+
+
+def test_deferred_tail_is_result_identical(gpu, s1_frames):
+    """defer_tail=1 (default): a call returns once the pose is known and the next call (or any look at the scene) runs
+    allocation .. model maps of that frame beside its own preprocessing.  Same bits as the strictly sequential frame."""
+    depth, _, _ = s1_frames
+    a = gpu.Context(corrected_mode=1, defer_tail=1)
+    b = gpu.Context(corrected_mode=1, defer_tail=0)
+    try:
+        for i in range(8):
+            assert a.process_frame(depth[i]) and b.process_frame(depth[i])
+            assert np.array_equal(a.pose().view(np.uint32), b.pose().view(np.uint32)), i
+            if i == 4:   # looking at the scene in the middle of the sequence finishes the pending tail first
+                assert a.voxel_updates() == b.voxel_updates() > 0
+                assert a.counters() == b.counters()
+        assert a.voxel_updates_total() + a.voxel_updates() == b.voxel_updates_total()   # the last tail is still pending in `a`
+        assert np.array_equal(a.raycast_result().view(np.uint32), b.raycast_result().view(np.uint32))
+        assert gpu.allocated_set(a.table()) == gpu.allocated_set(b.table())
+        ba, bb = a.blocks_by_pos(), b.blocks_by_pos()
+        assert set(ba) == set(bb)
+        for k in ba:
+            assert np.array_equal(ba[k]["sdf"], bb[k]["sdf"]) and np.array_equal(ba[k]["w"], bb[k]["w"])
+        assert np.array_equal(a.render_image(), b.render_image())
+    finally:
+        a.close(); b.close()

@@ -35,6 +35,7 @@ class Params(C.Structure):
         ("num_blocks", C.c_int32), ("num_buckets", C.c_int32), ("excess_size", C.c_int32),
         ("depth_cutoff_mm", C.c_int32), ("corrected_mode", C.c_int32),
         ("shard_rank", C.c_int32), ("shard_count", C.c_int32),
+        ("defer_tail", C.c_int32),
     ]
 
 
@@ -69,6 +70,8 @@ def lib() -> C.CDLL:
         L.tfb_last_error.restype = C.c_char_p
         L.tfb_version.restype = C.c_char_p
         L.tfb_voxel_updates_last.restype = C.c_longlong
+        L.tfb_voxel_updates_total.restype = C.c_longlong
+        L.tfb_voxel_updates_total.argtypes = [C.c_void_p]
         L.tfb_kernel_launches.restype = C.c_longlong
         L.tfb_level_ptr.restype = C.c_void_p
         L.tfb_ktiming_name.restype = C.c_char_p
@@ -372,6 +375,10 @@ class Context:
 
     def voxel_updates(self) -> int:
         return int(self.L.tfb_voxel_updates_last(self.h))
+
+    def voxel_updates_total(self) -> int:
+        """summed over every integration finished so far; never waits for a deferred tail"""
+        return int(self.L.tfb_voxel_updates_total(self.h))
 
     def kernel_launches(self) -> int:
         return int(self.L.tfb_kernel_launches(self.h))

@@ -31,7 +31,7 @@ cudaError_t dmalloc(T** p, size_t n) { return cudaMalloc((void**)p, n * sizeof(T
 void free_all(tfb_ctx* c) {
     cudaFree(c->table); cudaFree(c->vba); cudaFree(c->vba_free); cudaFree(c->excess_free);
     cudaFree(c->claim_key); cudaFree(c->claimed); cudaFree(c->bucket_bits); cudaFree(c->vis_type); cudaFree(c->vis_list[0]); cudaFree(c->vis_list[1]);
-    cudaFree(c->minmax); cudaFree(c->raycast); cudaFree(c->dists); cudaFree(c->depth_in); cudaFree(c->icp_partial);
+    cudaFree(c->minmax); cudaFree(c->raycast); cudaFree(c->dists_buf[0]); cudaFree(c->dists_buf[1]); cudaFree(c->depth_in); cudaFree(c->icp_partial);
     cudaFree(c->ds); cudaFree(c->l2_scratch); cudaFree(c->marks); cudaFree(c->shard_dev);
     for (int l = 0; l < MAX_LEVELS; ++l) {
         cudaFree(c->lv[l].depth); cudaFree(c->lv[l].vcurr); cudaFree(c->lv[l].ncurr); cudaFree(c->lv[l].vprev); cudaFree(c->lv[l].nprev);
@@ -48,6 +48,11 @@ void free_all(tfb_ctx* c) {
             if (c->kt_ev[i]) cudaEventDestroy(c->kt_ev[i]);
         free(c->kt_ev);
     }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->ev_pre0) cudaEventDestroy(c->ev_pre0);
+    if (c->ev_pre1) cudaEventDestroy(c->ev_pre1);
+    if (c->stream_pre) cudaStreamDestroy(c->stream_pre);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     free(c->poses);
 }
@@ -193,6 +198,7 @@ int frame_end(tfb_ctx* c, int* ok) {
         c->stage_ms[ST_FRAME] = t;
     }
     c->voxel_updates_last = (long long)c->hs->voxel_updates;
+    if (first || !c->hs->icp_failed) c->voxel_updates_total += c->voxel_updates_last;
     if (first) {
         c->frame_counter++;
         *ok = 1;
@@ -210,16 +216,127 @@ int frame_end(tfb_ctx* c, int* ok) {
     return TFB_OK;
 }
 
-int do_frame(tfb_ctx* c, const uint16_t* depth_dev, int* ok) {
+// allocation .. model maps of the frame whose pose the last ICP produced (topfu.cpp:266-327), on the main stream
+int enqueue_tail(tfb_ctx* c) {
+    int r;
+    c->tail_pending = false;
+    const float* dists = c->tail_dists;
+    stamp(c, ST_ALLOC);
+    if ((r = launch_allocate(c, dists))) return r;
+    stamp(c, ST_INTEG);
+    if ((r = launch_integrate(c, dists))) return r;
+    stamp(c, ST_EXPECT);
+    if ((r = launch_expected_depths(c))) return r;
+    stamp(c, ST_RAYCAST);
+    if ((r = launch_raycast(c, true))) return r;
+    if ((r = launch_model_maps(c))) return r;
+    stamp(c, ST_PYR);
+    return TFB_OK;
+}
+
+// every entry point that looks at (or changes) the scene, the lists or the model maps calls this first
+int settle(tfb_ctx* c) {
+    if (!c->tail_pending) return TFB_OK;
+    int r = enqueue_tail(c);
+    if (r) return r;
+    if ((r = fetch_state(c))) return r;   // counters and voxel-update count of the frame that has just been finished
+    c->voxel_updates_last = (long long)c->hs->voxel_updates;
+    c->voxel_updates_total += c->voxel_updates_last;
+    return TFB_OK;
+}
+
+// The unsharded frame, software-pipelined.  Per call:
+//     main stream   [tail of the previous frame: allocate, integrate, expected depths, raycast, model maps] -> ICP -> pose
+//     second stream [upload + preprocessing of this frame] -------------------------------------------------^
+// The reference runs the same stages strictly in sequence (topfu.cpp:161-330); the tail of frame k and the preprocessing
+// of frame k+1 are independent, and both leave most of the machine idle, so they share it.  Results are identical.
+int do_frame(tfb_ctx* c, const uint16_t* depth, size_t host_step_bytes, int* ok) {
     if (sharded(c))
         return set_err(c, TFB_ERR_STATE, "sharded context: drive the frame with tfb_frame_begin / _raycast / _end and a barrier between them");
+    if (c->frame_stage != 0) return set_err(c, TFB_ERR_STATE, "a staged frame is in progress (tfb_frame_end)");
     int r;
-    if ((r = frame_begin(c, depth_dev))) { c->frame_stage = 0; return r; }
-    if ((r = frame_raycast(c))) { c->frame_stage = 0; return r; }
-    return frame_end(c, ok);
+    const bool first = (c->frame_counter == 0);
+    stamp(c, ST_UPLOAD);
+    // the second stream starts where the caller's work on the main stream ends
+    TFB_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));
+    TFB_CUDA(c, cudaStreamWaitEvent(c->stream_pre, c->ev_fork, 0));
+    const bool had_tail = c->tail_pending;
+    if (had_tail) { if ((r = enqueue_tail(c))) return r; }
+    else { stamp(c, ST_ALLOC); stamp(c, ST_INTEG); stamp(c, ST_EXPECT); stamp(c, ST_RAYCAST); stamp(c, ST_PYR); }
+    // this frame's metres image must not overwrite the one the tail above is still reading
+    float* dists = (c->tail_dists == c->dists_buf[0]) ? c->dists_buf[1] : c->dists_buf[0];
+    c->dists = dists;
+    {
+        cudaStream_t main_stream = c->stream;
+        c->stream = c->stream_pre;   // the launchers enqueue on c->stream
+        if (c->timing) cudaEventRecord(c->ev_pre0, c->stream);
+        const uint16_t* src = depth;
+        cudaError_t e = cudaSuccess;
+        if (host_step_bytes) {
+            const size_t row = (size_t)c->p.cols * sizeof(uint16_t);
+            e = cudaMemcpy2DAsync(c->depth_in, row, depth, host_step_bytes, row, c->p.rows, cudaMemcpyHostToDevice, c->stream);
+            src = c->depth_in;
+        }
+        r = (e == cudaSuccess) ? do_preprocess(c, src, first) : set_err(c, TFB_ERR_CUDA, "frame upload", e);
+        if (c->timing) cudaEventRecord(c->ev_pre1, c->stream);
+        if (r == TFB_OK && cudaEventRecord(c->ev_join, c->stream) != cudaSuccess) r = set_err(c, TFB_ERR_CUDA, "event record");
+        c->stream = main_stream;
+        if (r) return r;
+    }
+    TFB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    stamp(c, ST_ICP);
+    if (first) {
+        // frame 0: no tracking; the maps went straight into the model pyramid (topfu.cpp:199-209)
+        c->tail_dists = dists;
+        if ((r = launch_allocate(c, dists))) return r;
+        if ((r = launch_integrate(c, dists))) return r;
+    } else if ((r = do_icp(c, true))) return r;
+    stamp(c, ST_FRAME);
+    if ((r = fetch_state(c))) return r;   // the one wait of the call: pose, verdict, counters
+    if (c->timing) {
+        float t = 0.f;
+        static const int seq[] = {ST_UPLOAD, ST_ALLOC, ST_INTEG, ST_EXPECT, ST_RAYCAST, ST_PYR, ST_ICP, ST_FRAME};
+        for (int i = 0; i + 1 < 8; ++i) {   // stage_ms[x] = time from stamp x to the next stamp on the main stream
+            cudaEventElapsedTime(&t, c->ev[seq[i]], c->ev[seq[i + 1]]);
+            c->stage_ms[seq[i]] = t;
+        }
+        c->stage_ms[ST_UPLOAD] = 0.f;
+        cudaEventElapsedTime(&t, c->ev_pre0, c->ev_pre1);
+        c->stage_ms[ST_PRE] = t;            // upload + preprocessing, on the second stream
+        cudaEventElapsedTime(&t, c->ev[ST_UPLOAD], c->ev[ST_FRAME]);
+        c->stage_ms[ST_FRAME] = t;
+    }
+    if (had_tail || first) {   // an integration finished inside this call: the previous frame's, or frame 0's
+        c->voxel_updates_last = (long long)c->hs->voxel_updates;
+        c->voxel_updates_total += c->voxel_updates_last;
+    }
+    if (first) {
+        c->frame_counter++;
+        *ok = 1;
+        return TFB_OK;
+    }
+    if (c->hs->icp_failed) {  // topfu.cpp:263-264: return reset(), false
+        c->voxel_updates_last = 0;
+        if ((r = do_reset(c))) return r;
+        *ok = 0;
+        return TFB_OK;
+    }
+    if ((r = push_pose(c, c->hs->pose_c2w))) return r;
+    c->frame_counter++;
+    *ok = 1;
+    c->tail_pending = true;
+    c->tail_dists = dists;
+    if (!c->p.defer_tail) return settle(c);
+    return TFB_OK;
 }
 
 }  // namespace
+
+#define TFB_SETTLE(c)                       \
+    do {                                    \
+        int r__ = settle(c);                \
+        if (r__ != TFB_OK) return r__;      \
+    } while (0)
 
 extern "C" {
 
@@ -238,6 +355,7 @@ int tfb_default_params(tfb_params* p) {
     p->num_blocks = 0x10000; p->num_buckets = 0x100000; p->excess_size = 0x20000;  // VoxelBlockHash.hpp:14-18
     p->depth_cutoff_mm = 2047;
     p->corrected_mode = 0; p->shard_rank = 0; p->shard_count = 1;
+    p->defer_tail = 1;
     return TFB_OK;
 }
 
@@ -278,7 +396,14 @@ int tfb_create(const tfb_params* p, void* stream, tfb_ctx** out) {
     ok(dmalloc(&c->vis_list[1], (size_t)c->total_entries));
     ok(dmalloc(&c->minmax, npx / (MINMAX_SUB * MINMAX_SUB)));
     ok(dmalloc(&c->raycast, npx));
-    ok(dmalloc(&c->dists, npx));
+    ok(dmalloc(&c->dists_buf[0], npx));
+    ok(dmalloc(&c->dists_buf[1], npx));
+    c->dists = c->dists_buf[0];
+    ok(cudaStreamCreateWithFlags(&c->stream_pre, cudaStreamNonBlocking));
+    ok(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    ok(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    ok(cudaEventCreate(&c->ev_pre0));
+    ok(cudaEventCreate(&c->ev_pre1));
     ok(dmalloc(&c->depth_in, npx));
     {
         int w = p->cols, h = p->rows;
@@ -319,7 +444,8 @@ int tfb_create(const tfb_params* p, void* stream, tfb_ctx** out) {
     cudaMemsetAsync(c->vis_type, 0, (size_t)c->total_entries * sizeof(int), c->stream);
     cudaMemsetAsync(c->claim_key, 0, (size_t)c->total_entries * sizeof(unsigned), c->stream);
     cudaMemsetAsync(c->raycast, 0, npx * sizeof(float4), c->stream);
-    cudaMemsetAsync(c->dists, 0, npx * sizeof(float), c->stream);
+    cudaMemsetAsync(c->dists_buf[0], 0, npx * sizeof(float), c->stream);
+    cudaMemsetAsync(c->dists_buf[1], 0, npx * sizeof(float), c->stream);
     {   // RenderState ctor fills the range image with (vf_min, vf_max), include/tfusion/RenderState.hpp:67-73
         size_t n = npx / (MINMAX_SUB * MINMAX_SUB);
         float2* tmp = (float2*)malloc(n * sizeof(float2));
@@ -344,6 +470,8 @@ int tfb_create(const tfb_params* p, void* stream, tfb_ctx** out) {
 
 int tfb_destroy(tfb_ctx* c) {
     if (!c) return TFB_ERR_ARG;
+    c->tail_pending = false;   // nobody can look at the scene any more
+    cudaStreamSynchronize(c->stream_pre);
     cudaStreamSynchronize(c->stream);
     free_all(c);
     delete c;
@@ -352,6 +480,7 @@ int tfb_destroy(tfb_ctx* c) {
 
 int tfb_reset(tfb_ctx* c) {
     if (!c) return TFB_ERR_ARG;
+    TFB_SETTLE(c);
     int r = do_reset(c);
     if (r) return r;
     TFB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -372,12 +501,14 @@ int tfb_h2d(tfb_ctx* c, void* dst, const void* src, size_t bytes) {
 }
 int tfb_d2h(tfb_ctx* c, void* dst, const void* src, size_t bytes) {
     if (!c || !dst || !src) return TFB_ERR_ARG;
+    TFB_SETTLE(c);
     TFB_CUDA(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
     TFB_CUDA(c, cudaStreamSynchronize(c->stream));
     return TFB_OK;
 }
 int tfb_sync(tfb_ctx* c) {
     if (!c) return TFB_ERR_ARG;
+    TFB_SETTLE(c);
     TFB_CUDA(c, cudaStreamSynchronize(c->stream));
     return TFB_OK;
 }
@@ -410,6 +541,7 @@ int tfb_resize_points_normals(tfb_ctx* c, const float* points, const float* norm
 }
 int tfb_preprocess(tfb_ctx* c, const uint16_t* depth_dev) {
     if (!c || !depth_dev) return TFB_ERR_ARG;
+    TFB_SETTLE(c);
     return do_preprocess(c, depth_dev, false);
 }
 
@@ -417,6 +549,7 @@ int tfb_preprocess(tfb_ctx* c, const uint16_t* depth_dev) {
 int tfb_icp_reduce(tfb_ctx* c, int cols, int rows, float fx, float fy, float cx, float cy, const float aff[16], const float* vcurr,
                    const float* ncurr, const float* vprev, const float* nprev, float out27_host[27]) {
     if (!c || !aff || !vcurr || !ncurr || !vprev || !nprev || !out27_host) return TFB_ERR_ARG;
+    TFB_SETTLE(c);
     int r = launch_icp_begin(c);
     if (r) return r;
     TFB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -434,6 +567,7 @@ int tfb_icp_reduce(tfb_ctx* c, int cols, int rows, float fx, float fy, float cx,
 
 int tfb_icp_estimate(tfb_ctx* c, float affine_out[16], int* ok) {
     if (!c || !affine_out || !ok) return TFB_ERR_ARG;
+    TFB_SETTLE(c);
     int r = do_icp(c, false);
     if (r) return r;
     if ((r = fetch_state(c))) return r;
@@ -445,12 +579,14 @@ int tfb_icp_estimate(tfb_ctx* c, float affine_out[16], int* ok) {
 // ---- scene / visualisation stages with an injected pose ------------------------------------------------
 int tfb_allocate_scene_from_depth(tfb_ctx* c, const float pose_w2c[16], const float* dists_dev) {
     if (!c || !pose_w2c || !dists_dev) return TFB_ERR_ARG;
+    TFB_SETTLE(c);
     int r = launch_pose_set(c, pose_w2c, true);
     if (r) return r;
     return launch_allocate(c, dists_dev);
 }
 int tfb_integrate_into_scene(tfb_ctx* c, const float pose_w2c[16], const float* dists_dev) {
     if (!c || !pose_w2c || !dists_dev) return TFB_ERR_ARG;
+    TFB_SETTLE(c);
     int r = launch_pose_set(c, pose_w2c, true);
     if (r) return r;
     TFB_CUDA(c, cudaMemsetAsync(&c->ds->voxel_updates, 0, sizeof(unsigned long long), c->stream));
@@ -462,12 +598,14 @@ int tfb_integrate_into_scene(tfb_ctx* c, const float pose_w2c[16], const float* 
 }
 int tfb_create_expected_depths(tfb_ctx* c, const float pose_w2c[16]) {
     if (!c || !pose_w2c) return TFB_ERR_ARG;
+    TFB_SETTLE(c);
     int r = launch_pose_set(c, pose_w2c, true);
     if (r) return r;
     return launch_expected_depths(c, true);
 }
 int tfb_create_icp_maps(tfb_ctx* c, const float pose_c2w[16], float* points_dev, float* normals_dev) {
     if (!c || !pose_c2w || !points_dev || !normals_dev) return TFB_ERR_ARG;
+    TFB_SETTLE(c);
     int r = launch_pose_set(c, pose_c2w, false);
     if (r) return r;
     return launch_icp_maps(c, (float4*)points_dev, (float4*)normals_dev);
@@ -475,6 +613,7 @@ int tfb_create_icp_maps(tfb_ctx* c, const float pose_c2w[16], float* points_dev,
 
 int tfb_render_image(tfb_ctx* c, const float* pose_c2w_or_null, uint8_t* rgba_dev) {
     if (!c || !rgba_dev) return TFB_ERR_ARG;
+    TFB_SETTLE(c);
     if (pose_c2w_or_null) {
         int r = launch_pose_set(c, pose_c2w_or_null, false);
         if (r) return r;
@@ -486,6 +625,7 @@ int tfb_icp_estimate_ext(tfb_ctx* c, int levels, const float* const* vcurr, cons
                          const float* const* nprev, int cols, int rows, const int* iters, float dist_thres, float angle_thres,
                          const float intr_or_null[4], float affine_out[16], int* ok) {
     if (!c || !vcurr || !ncurr || !vprev || !nprev || !iters || !affine_out || !ok) return TFB_ERR_ARG;
+    TFB_SETTLE(c);
     tfb_params saved = c->p;
     if (intr_or_null) { c->p.fx = intr_or_null[0]; c->p.fy = intr_or_null[1]; c->p.cx = intr_or_null[2]; c->p.cy = intr_or_null[3]; }
     int r = launch_icp_all_ext(c, levels, vcurr, ncurr, vprev, nprev, cols, rows, iters, dist_thres, angle_thres);
@@ -542,15 +682,12 @@ int tfb_process_frame(tfb_ctx* c, const uint16_t* depth_host, size_t step_bytes,
     const size_t row = (size_t)c->p.cols * sizeof(uint16_t);
     if (step_bytes == 0) step_bytes = row;
     if (step_bytes < row) return TFB_ERR_ARG;
-    stamp(c, ST_UPLOAD);
-    TFB_CUDA(c, cudaMemcpy2DAsync(c->depth_in, row, depth_host, step_bytes, row, c->p.rows, cudaMemcpyHostToDevice, c->stream));
-    return do_frame(c, c->depth_in, ok);
+    return do_frame(c, depth_host, step_bytes, ok);
 }
 
 int tfb_process_frame_device(tfb_ctx* c, const uint16_t* depth_dev, int* ok) {
     if (!c || !depth_dev || !ok) return TFB_ERR_ARG;
-    stamp(c, ST_UPLOAD);
-    return do_frame(c, depth_dev, ok);
+    return do_frame(c, depth_dev, 0, ok);
 }
 
 int tfb_get_pose(const tfb_ctx* c, int time, float out16[16]) {
@@ -599,6 +736,7 @@ int tfb_ipc_close(void* dev_ptr) { return cudaIpcCloseMemHandle(dev_ptr) == cuda
 
 int tfb_frame_begin(tfb_ctx* c, const uint16_t* depth_dev) {
     if (!c || !depth_dev) return TFB_ERR_ARG;
+    TFB_SETTLE(c);
     stamp(c, ST_UPLOAD);
     return frame_begin(c, depth_dev);
 }
@@ -609,6 +747,7 @@ void* tfb_stream(tfb_ctx* c) { return c ? (void*)c->stream : nullptr; }
 // ---- inspection -----------------------------------------------------------------------------------------
 int tfb_get_counters(tfb_ctx* c, long long out[8]) {
     if (!c || !out) return TFB_ERR_ARG;
+    TFB_SETTLE(c);
     int r = fetch_state(c);
     if (r) return r;
     out[0] = c->hs->n_visible; out[1] = c->hs->last_free_block; out[2] = c->hs->last_free_excess; out[3] = c->hs->n_new_frame;
@@ -616,7 +755,12 @@ int tfb_get_counters(tfb_ctx* c, long long out[8]) {
     out[7] = (long long)c->p.num_blocks - 1 - c->hs->last_free_block;
     return TFB_OK;
 }
-long long tfb_voxel_updates_last(tfb_ctx* c) { return c ? c->voxel_updates_last : 0; }
+long long tfb_voxel_updates_last(tfb_ctx* c) {
+    if (!c) return 0;
+    settle(c);
+    return c->voxel_updates_last;
+}
+long long tfb_voxel_updates_total(const tfb_ctx* c) { return c ? c->voxel_updates_total : 0; }
 int tfb_total_entries(const tfb_ctx* c) { return c ? c->total_entries : 0; }
 
 int tfb_export_table(tfb_ctx* c, void* host) {
@@ -635,6 +779,7 @@ int tfb_export_vis_type(tfb_ctx* c, uint8_t* host) {
 }
 int tfb_export_visible_ids(tfb_ctx* c, int32_t* host, int capacity, int* n) {
     if (!c || !host || !n) return TFB_ERR_ARG;
+    TFB_SETTLE(c);
     int r = fetch_state(c);
     if (r) return r;
     *n = c->hs->n_visible;
@@ -661,6 +806,7 @@ int tfb_export_dists(tfb_ctx* c, float* host) {
 
 void* tfb_level_ptr(tfb_ctx* c, int which, int level) {
     if (!c || level < 0 || level >= MAX_LEVELS) return nullptr;
+    if (settle(c) != TFB_OK) return nullptr;
     switch (which) {
         case 0: return c->lv[level].depth;
         case 1: return c->lv[level].vcurr;
@@ -683,6 +829,7 @@ int tfb_export_level(tfb_ctx* c, int which, int level, void* host) {
     return tfb_d2h(c, host, p, level_bytes(c, which, level));
 }
 int tfb_import_level(tfb_ctx* c, int which, int level, const void* host) {
+    if (c) TFB_SETTLE(c);
     void* p = tfb_level_ptr(c, which, level);
     if (!p || !host) return TFB_ERR_ARG;
     TFB_CUDA(c, cudaMemcpyAsync(p, host, level_bytes(c, which, level), cudaMemcpyHostToDevice, c->stream));

@@ -130,7 +130,8 @@ struct tfb_ctx {
     float4* raycast;           // rows x cols
     // frames
     tfb::LevelBuf lv[tfb::MAX_LEVELS];
-    float* dists;
+    float* dists;              // metres image of the frame being tracked (one of dists_buf, alternating per frame)
+    float* dists_buf[2];
     uint16_t* depth_in;        // device copy of the raw frame
     // ICP
     float* icp_partial;        // [ICP_TERMS][max_blocks]
@@ -149,6 +150,7 @@ struct tfb_ctx {
     int n_poses, cap_poses;
     long long launches;
     long long voxel_updates_last;
+    long long voxel_updates_total;   // over every integration finished so far
 
     // timing
     bool timing;
@@ -171,6 +173,11 @@ struct tfb_ctx {
     unsigned int* marks;       // incoming visibility marks: [0] count, [1] pad, then 2 words per mark
     int frame_stage;           // 0 idle, 1 after tfb_frame_begin, 2 after tfb_frame_raycast
     bool frame_first;
+    // software pipeline of the unsharded frame: preprocessing runs on stream_pre beside the deferred tail
+    cudaStream_t stream_pre;
+    cudaEvent_t ev_fork, ev_join, ev_pre0, ev_pre1;
+    bool tail_pending;         // allocation .. model maps of the last tracked frame are still to be enqueued
+    const float* tail_dists;
 };
 
 namespace tfb {
