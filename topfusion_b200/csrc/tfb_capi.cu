@@ -589,7 +589,7 @@ int tfb_integrate_into_scene(tfb_ctx* c, const float pose_w2c[16], const float* 
     TFB_SETTLE(c);
     int r = launch_pose_set(c, pose_w2c, true);
     if (r) return r;
-    TFB_CUDA(c, cudaMemsetAsync(&c->ds->voxel_updates, 0, sizeof(unsigned long long), c->stream));
+    TFB_CUDA(c, cudaMemsetAsync(&c->ds->voxel_updates, 0, sizeof(unsigned long long) + 2 * sizeof(int), c->stream));  // + ticket, cursor
     r = launch_integrate(c, dists_dev);
     if (r) return r;
     if ((r = fetch_state(c))) return r;

@@ -71,7 +71,7 @@ struct DevState {
     // statistics
     unsigned long long voxel_updates;
     unsigned int list_ticket;   // CTAs of k_visible_list that are done; the last one flips the lists
-    int pad_[1];
+    int int_cursor;             // next visible-list position k_integrate hands out
 };
 
 // payload owner of a block when the scene is sharded (new; the reference is single-GPU).  A different mix than
