@@ -1,0 +1,124 @@
+"""GPU parity on the larger BASELINE.json configurations (they are parity cases, not bench lines):
+  configs[2]  1280x720 room walk-through (S2), 4 mm voxels, 2^22-bucket hash
+  configs[3]  large scene (S3), 2 mm voxels, the scene sharded by block hash (two ranks emulated on one GPU)
+Stages with injected ground-truth poses must be bit-exact against the oracle; the tracked frame path must keep the
+pose within 1e-4 m / 1e-4 rad of the oracle's."""
+import numpy as np
+import pytest
+
+from conftest import same_bits_nan
+
+pytestmark = pytest.mark.gpu
+
+
+def _digest(blocks):
+    """{pos: (sum sdf, sum w, xor-fold)} — cheap per-block fingerprint for tens of thousands of blocks"""
+    out = {}
+    for pos, v in blocks.items():
+        s = v["sdf"].astype(np.int64)
+        out[pos] = (int(s.sum()), int(v["w"].astype(np.int64).sum()), int(np.bitwise_xor.reduce(s * 31 + v["w"])))
+    return out
+
+
+def test_config3_room_1280x720_stages_bit_exact(gpu):
+    from oracle import tfo
+    from topfusion_b200 import synth
+    depth, poses, intr = synth.sequence("S2", 3)
+    kw = dict(cols=1280, rows=720, fx=intr[0], fy=intr[1], cx=intr[2], cy=intr[3], voxel_size=0.004, mu=0.016,
+              num_blocks=1 << 18, num_buckets=1 << 22, excess_size=1 << 18, depth_cutoff_mm=4000, view_frustum_max=4.0)
+    L = tfo.Lib("port")
+    o = tfo.Oracle(lib=L, **kw)
+    g = gpu.Context(**kw)
+    try:
+        for i in range(3):
+            dists = L.compute_dists(depth[i], 4000)
+            c2w = poses[i].astype(np.float32)
+            w2c = L.pose_inv(c2w)
+            o.allocate(w2c, dists); g.allocate(w2c, dists)
+            o.integrate(w2c, dists); g.integrate(w2c, dists)
+            assert o.voxel_updates() == g.voxel_updates() > 512 * 20000, i
+            o.expected_depths(w2c); g.expected_depths(w2c)
+            (op, on), (gp, gn) = o.icp_maps(c2w), g.icp_maps(c2w)
+            assert np.array_equal(o.raycast_result().view(np.uint32), g.raycast_result().view(np.uint32)), i
+            assert same_bits_nan(op, gp).all() and same_bits_nan(on, gn).all(), i   # NaN marks invalid pixels (payload differs)
+        to, tg = o.table(), g.table()
+        assert tfo.allocated_set(to) == gpu.allocated_set(tg)
+        assert tfo.visible_set(to, o.visible_ids()) == gpu.visible_set(tg, g.visible_ids())
+        co, cg = o.counters(), g.counters()
+        for k in ("n_visible", "last_free_block", "last_free_excess", "n_allocated"):
+            assert co[k] == cg[k], k
+        # every 7th block, voxel for voxel
+        po = {tuple(int(v) for v in e["pos"]): int(e["ptr"]) for e in to[to["ptr"] >= 0]}
+        pg = {tuple(int(v) for v in e["pos"]): int(e["ptr"]) for e in tg[tg["ptr"] >= 0]}
+        for pos in sorted(po)[::7]:
+            bo, bg = o.block(po[pos]), g.block(pg[pos])
+            assert np.array_equal(bo["sdf"], bg["sdf"]) and np.array_equal(bo["w"], bg["w"]), pos
+    finally:
+        g.close(); o.close()
+
+
+def test_config3_room_1280x720_tracked_frames(gpu):
+    from oracle import tfo
+    from topfusion_b200 import synth
+    depth, poses, intr = synth.sequence("S2", 4)
+    kw = dict(cols=1280, rows=720, fx=intr[0], fy=intr[1], cx=intr[2], cy=intr[3], voxel_size=0.004, mu=0.016,
+              num_blocks=1 << 18, num_buckets=1 << 22, excess_size=1 << 18, depth_cutoff_mm=4000, view_frustum_max=4.0,
+              icp_truncate_depth_dist=4.0, corrected_mode=1)
+    o = tfo.Oracle(**kw)
+    g = gpu.Context(**kw)
+    try:
+        for i in range(4):
+            ok_o, ok_g = o.process_frame(depth[i]), g.process_frame(depth[i])
+            assert ok_o and ok_g, i
+            po, pg = o.pose(), g.pose()
+            assert np.abs(po[:3, 3] - pg[:3, 3]).max() < 1e-4, (i, po[:3, 3], pg[:3, 3])
+            D = po[:3, :3].astype(np.float64).T @ pg[:3, :3].astype(np.float64)
+            w = 0.5 * np.array([D[2, 1] - D[1, 2], D[0, 2] - D[2, 0], D[1, 0] - D[0, 1]])
+            assert np.linalg.norm(w) < 1e-4, i
+            assert np.abs(pg[:3, 3] - poses[i][:3, 3]).max() < 5e-3, (i, "does not track the walk")
+    finally:
+        g.close(); o.close()
+
+
+def test_config4_large_scene_2mm_sharded_bit_exact(gpu):
+    """S3 at 2 mm voxels: two shards (emulated ranks, attached by device pointers) against ONE oracle scene."""
+    from oracle import tfo
+    from topfusion_b200 import synth
+    from test_gpu_sharding import make_shards
+    depth, poses, intr = synth.sequence("S3", 2)
+    kw = dict(voxel_size=0.002, mu=0.008, num_blocks=1 << 19, num_buckets=1 << 22, excess_size=1 << 18, depth_cutoff_mm=4000)
+    L = tfo.Lib("port")
+    o = tfo.Oracle(lib=L, **kw)
+    ctxs = make_shards(gpu, 2, **kw)
+    try:
+        for i in range(2):
+            dists = L.compute_dists(depth[i], 4000)
+            w2c = L.pose_inv(poses[i].astype(np.float32))
+            o.allocate(w2c, dists); o.integrate(w2c, dists)
+            upd = 0
+            for c in ctxs:
+                c.allocate(w2c, dists); c.integrate(w2c, dists)
+                upd += c.voxel_updates()
+            assert upd == o.voxel_updates() > 512 * 20000, (i, upd, o.voxel_updates())
+        to = o.table()
+        ref_alloc = tfo.allocated_set(to)
+        po = {tuple(int(v) for v in e["pos"]): int(e["ptr"]) for e in to[to["ptr"] >= 0]}
+        owned = {}
+        for r, c in enumerate(ctxs):
+            t = c.table()
+            assert gpu.allocated_set(t) == ref_alloc, "the index must be a replica on every rank"
+            for e in t[t["ptr"] >= 0]:
+                pos = tuple(int(v) for v in e["pos"])
+                assert pos not in owned
+                owned[pos] = (r, int(e["ptr"]))
+        assert set(owned) == set(po)
+        for pos in sorted(po)[::23]:
+            r, ptr = owned[pos]
+            bo, bg = o.block(po[pos]), ctxs[r].block(ptr)
+            assert np.array_equal(bo["sdf"], bg["sdf"]) and np.array_equal(bo["w"], bg["w"]), pos
+        n0 = sum(1 for v in owned.values() if v[0] == 0)
+        assert 0.45 < n0 / len(owned) < 0.55, "the owner mix must balance the shards"
+    finally:
+        for c in reversed(ctxs):
+            c.close()
+        o.close()
