@@ -324,6 +324,9 @@ def main():
         b.free()
     pin.free()
 
+    from topfusion_b200 import multigpu
+    large = multigpu.integrate_scaling_leg(0, 1)
+
     line = {
         "metric": "frames/sec (ICP+integrate+raycast, 640x480)",
         "value": fps, "unit": "frames/s", "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": total_ms / K,
@@ -338,6 +341,7 @@ def main():
         "roofline": roof,
         "cpu_baseline": cpu,
         "voxel_updates_per_s": vox / (total_ms / 1000.0),
+        "voxel_updates_large_scene": large,
         "warm_l2_value": K / (warm_ms / 1000.0),
         "kernels": table,
         "bandwidth_kernels": extra,

@@ -188,12 +188,24 @@ typedef struct tfb_shard_ptrs {
     void* vba;       /* num_blocks x 2 KB voxel pool */
     void* raycast;   /* rows x cols float4 raycast result */
     void* marks;     /* incoming visibility marks: u32 count, pad, then 2 x u32 per mark */
+    void* frame;     /* rows x cols u16: the depth frame rank 0 pushes to every rank (tfb_shard_push_frame) */
+    void* flags;     /* TFB_MAX_SHARDS x u32: flags[r] = last barrier epoch rank r has reached (tfb_shard_barrier) */
 } tfb_shard_ptrs;
 TFB_API int tfb_shard_local_ptrs(tfb_ctx* c, tfb_shard_ptrs* out);
 TFB_API int tfb_shard_attach(tfb_ctx* c, int rank, const tfb_shard_ptrs* peer);
 TFB_API int tfb_ipc_export(const void* dev_ptr, unsigned char handle64[64]);   /* cudaIpcGetMemHandle */
 TFB_API int tfb_ipc_open(const unsigned char handle64[64], void** dev_ptr);    /* cudaIpcOpenMemHandle, peer access enabled */
 TFB_API int tfb_ipc_close(void* dev_ptr);
+/* Cross-GPU plumbing over the same peer pointers, ON THE CONTEXT STREAM (no host synchronisation, no NCCL call):
+ * tfb_shard_push_frame  rank 0 only: one kernel stores its device frame into every rank's frame buffer (NVLink stores);
+ * tfb_shard_barrier     every rank: one warp publishes this rank's epoch into every rank's flag array with system-scope
+ *                       release stores and waits until every rank has published it.  Real multi-GPU only: the ranks'
+ *                       kernels wait on one another, so every rank must own a GPU (never two ranks on one device — the
+ *                       single-process emulation orders the stages by stream order instead).  A rank that waits longer
+ *                       than ~2 s gives up; the next tfb_frame_end reports TFB_ERR_STATE.
+ * tfb_frame_begin(c, NULL) then tracks the frame in the context's frame buffer. */
+TFB_API int tfb_shard_push_frame(tfb_ctx* c, const uint16_t* depth_dev);
+TFB_API int tfb_shard_barrier(tfb_ctx* c);
 TFB_API int tfb_frame_begin(tfb_ctx* c, const uint16_t* depth_dev);
 TFB_API int tfb_frame_raycast(tfb_ctx* c);
 TFB_API int tfb_frame_end(tfb_ctx* c, int* ok);

@@ -22,7 +22,7 @@ def main():
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
     n = int(os.environ.get("TFB_CHECK_FRAMES", "12"))
     depth, _, _ = synth.sequence("S1", n)
-    eng = multigpu.CudaEngine(rank, world, local, dist, corrected_mode=1)
+    eng = multigpu.CudaEngine(rank, world, local, dist, plumbing=os.environ.get("TFB_PLUMBING", "p2p"), corrected_mode=1)
     single = capi.Context(corrected_mode=1) if rank == 0 else None
     bad = 0
     with torch.cuda.stream(eng.stream):

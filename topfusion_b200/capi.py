@@ -41,7 +41,8 @@ class Params(C.Structure):
 
 class ShardPtrs(C.Structure):
     """tfb_shard_ptrs: the buffers of one rank that the other ranks read / write over peer memory"""
-    _fields_ = [("table", C.c_void_p), ("vba", C.c_void_p), ("raycast", C.c_void_p), ("marks", C.c_void_p)]
+    _fields_ = [("table", C.c_void_p), ("vba", C.c_void_p), ("raycast", C.c_void_p), ("marks", C.c_void_p),
+                ("frame", C.c_void_p), ("flags", C.c_void_p)]
 
 
 class TfbError(RuntimeError):
@@ -95,6 +96,8 @@ def lib() -> C.CDLL:
             "tfb_ipc_close": [C.c_void_p],
             "tfb_frame_begin": [C.c_void_p, C.c_void_p],
             "tfb_frame_raycast": [C.c_void_p],
+            "tfb_shard_push_frame": [C.c_void_p, C.c_void_p],
+            "tfb_shard_barrier": [C.c_void_p],
             "tfb_frame_end": [C.c_void_p, C.POINTER(C.c_int)],
         }.items():
             getattr(L, name).argtypes = args
@@ -345,9 +348,17 @@ class Context:
     def shard_attach(self, rank: int, ptrs: ShardPtrs):
         self._ck(self.L.tfb_shard_attach(self.h, C.c_int(rank), C.byref(ptrs)))
 
-    def frame_begin(self, dev_ptr):
-        p = dev_ptr.ptr if isinstance(dev_ptr, DevBuf) else C.c_void_p(dev_ptr)
+    def frame_begin(self, dev_ptr=None):
+        """dev_ptr None: the frame rank 0 pushed into this context's frame buffer (shard_push_frame)"""
+        p = None if dev_ptr is None else (dev_ptr.ptr if isinstance(dev_ptr, DevBuf) else C.c_void_p(dev_ptr))
         self._ck(self.L.tfb_frame_begin(self.h, p))
+
+    def shard_push_frame(self, dev_ptr):
+        p = dev_ptr.ptr if isinstance(dev_ptr, DevBuf) else C.c_void_p(dev_ptr)
+        self._ck(self.L.tfb_shard_push_frame(self.h, p))
+
+    def shard_barrier(self):
+        self._ck(self.L.tfb_shard_barrier(self.h))
 
     def frame_raycast(self):
         self._ck(self.L.tfb_frame_raycast(self.h))

@@ -32,7 +32,7 @@ void free_all(tfb_ctx* c) {
     cudaFree(c->table); cudaFree(c->vba); cudaFree(c->vba_free); cudaFree(c->excess_free);
     cudaFree(c->claim_key); cudaFree(c->claimed); cudaFree(c->bucket_bits); cudaFree(c->vis_type); cudaFree(c->vis_list[0]); cudaFree(c->vis_list[1]);
     cudaFree(c->minmax); cudaFree(c->raycast); cudaFree(c->dists_buf[0]); cudaFree(c->dists_buf[1]); cudaFree(c->depth_in); cudaFree(c->icp_partial);
-    cudaFree(c->ds); cudaFree(c->l2_scratch); cudaFree(c->marks); cudaFree(c->shard_dev);
+    cudaFree(c->ds); cudaFree(c->l2_scratch); cudaFree(c->marks); cudaFree(c->shard_dev); cudaFree(c->sync_flags);
     for (int l = 0; l < MAX_LEVELS; ++l) {
         cudaFree(c->lv[l].depth); cudaFree(c->lv[l].vcurr); cudaFree(c->lv[l].ncurr); cudaFree(c->lv[l].vprev); cudaFree(c->lv[l].nprev);
     }
@@ -186,6 +186,7 @@ int frame_end(tfb_ctx* c, int* ok) {
     }
     stamp(c, ST_FRAME);
     if ((r = fetch_state(c))) return r;  // the one wait of the frame
+    if (c->hs->shard_error) return set_err(c, TFB_ERR_STATE, "a cross-GPU barrier timed out: another rank stopped");
     if (c->timing) {
         float t;
         for (int i = ST_PRE; i < ST_FRAME; ++i) {
@@ -426,6 +427,7 @@ int tfb_create(const tfb_params* p, void* stream, tfb_ctx** out) {
     ok(cudaMalloc((void**)&c->ds, sizeof(DevState) + 64 * sizeof(float)));
     ok(cudaMalloc((void**)&c->marks, (size_t)(2 + 2 * MARKS_CAP) * sizeof(unsigned int)));
     ok(cudaMalloc((void**)&c->shard_dev, sizeof(ShardView)));
+    ok(cudaMalloc((void**)&c->sync_flags, TFB_MAX_SHARDS * sizeof(unsigned int)));
     ok(cudaMallocHost((void**)&c->hs, sizeof(DevState)));
     ok(cudaMallocHost((void**)&c->h_pose_stage, 64 * sizeof(float)));
     ok(cudaMallocHost((void**)&c->h_icp27, 32 * sizeof(float)));
@@ -454,6 +456,7 @@ int tfb_create(const tfb_params* p, void* stream, tfb_ctx** out) {
         free(tmp);
     }
     cudaMemsetAsync(c->marks, 0, 2 * sizeof(unsigned int), c->stream);
+    cudaMemsetAsync(c->sync_flags, 0, TFB_MAX_SHARDS * sizeof(unsigned int), c->stream);
     c->shard.rank = p->shard_rank; c->shard.count = p->shard_count; c->shard.marks_cap = MARKS_CAP;
     {
         tfb_shard_ptrs self;
@@ -703,15 +706,18 @@ int tfb_num_poses(const tfb_ctx* c) { return c ? c->n_poses : 0; }
 int tfb_shard_local_ptrs(tfb_ctx* c, tfb_shard_ptrs* out) {
     if (!c || !out) return TFB_ERR_ARG;
     out->table = c->table; out->vba = c->vba; out->raycast = c->raycast; out->marks = c->marks;
+    out->frame = c->depth_in; out->flags = c->sync_flags;
     return TFB_OK;
 }
 int tfb_shard_attach(tfb_ctx* c, int rank, const tfb_shard_ptrs* peer) {
     if (!c || !peer || rank < 0 || rank >= c->p.shard_count) return TFB_ERR_ARG;
-    if (!peer->table || !peer->vba || !peer->raycast || !peer->marks) return TFB_ERR_ARG;
+    if (!peer->table || !peer->vba || !peer->raycast || !peer->marks || !peer->frame || !peer->flags) return TFB_ERR_ARG;
     c->shard.table[rank] = (const int4*)peer->table;
     c->shard.vba[rank] = (const unsigned int*)peer->vba;
     c->shard.raycast[rank] = (float4*)peer->raycast;
     c->shard.marks[rank] = (unsigned int*)peer->marks;
+    c->shard.frame[rank] = (uint16_t*)peer->frame;
+    c->shard.flags[rank] = (unsigned int*)peer->flags;
     c->attached |= 1u << rank;
     TFB_CUDA(c, cudaStreamSynchronize(c->stream));   // a kernel may still be reading the device copy
     TFB_CUDA(c, cudaMemcpy(c->shard_dev, &c->shard, sizeof(ShardView), cudaMemcpyHostToDevice));
@@ -735,10 +741,20 @@ int tfb_ipc_open(const unsigned char handle64[64], void** dev_ptr) {
 int tfb_ipc_close(void* dev_ptr) { return cudaIpcCloseMemHandle(dev_ptr) == cudaSuccess ? TFB_OK : TFB_ERR_CUDA; }
 
 int tfb_frame_begin(tfb_ctx* c, const uint16_t* depth_dev) {
-    if (!c || !depth_dev) return TFB_ERR_ARG;
+    if (!c) return TFB_ERR_ARG;
     TFB_SETTLE(c);
     stamp(c, ST_UPLOAD);
-    return frame_begin(c, depth_dev);
+    return frame_begin(c, depth_dev ? depth_dev : c->depth_in);
+}
+int tfb_shard_push_frame(tfb_ctx* c, const uint16_t* depth_dev) {
+    if (!c || !depth_dev) return TFB_ERR_ARG;
+    if (c->attached != (1u << c->p.shard_count) - 1u) return set_err(c, TFB_ERR_STATE, "attach every rank's buffers first (tfb_shard_attach)");
+    return launch_shard_push_frame(c, depth_dev);
+}
+int tfb_shard_barrier(tfb_ctx* c) {
+    if (!c) return TFB_ERR_ARG;
+    if (c->attached != (1u << c->p.shard_count) - 1u) return set_err(c, TFB_ERR_STATE, "attach every rank's buffers first (tfb_shard_attach)");
+    return c->p.shard_count > 1 ? launch_shard_barrier(c) : TFB_OK;
 }
 int tfb_frame_raycast(tfb_ctx* c) { return c ? frame_raycast(c) : TFB_ERR_ARG; }
 int tfb_frame_end(tfb_ctx* c, int* ok) { return (c && ok) ? frame_end(c, ok) : TFB_ERR_ARG; }
@@ -879,7 +895,7 @@ static const char* const KNAMES[K_COUNT] = {
     "k_icp_begin", "k_icp_iteration[L0]", "k_icp_iteration[L1]", "k_icp_iteration[L2]", "k_icp_iteration[L3]", "(unused)",
     "k_pose_set", "k_set_type3", "k_mark", "k_alloc", "k_visible_list", "k_list_flip", "k_integrate_begin", "k_integrate",
     "k_minmax_init", "k_expected_depths", "k_raycast", "k_icp_maps", "k_reset_scene", "k_icp_all", "k_render_grey",
-    "k_raycast_sharded", "k_apply_marks", "k_model_maps", "k_pyramid_maps"};
+    "k_raycast_sharded", "k_apply_marks", "k_model_maps", "k_pyramid_maps", "k_shard_barrier", "k_push_frame"};
 
 int tfb_ktiming_enable(tfb_ctx* c, int on) {
     if (!c) return TFB_ERR_ARG;

@@ -14,7 +14,7 @@ enum KernelId {
     K_BILATERAL = 0, K_DEPTH_PYR, K_POINTS_NORMALS, K_RESIZE_MAPS, K_COMPUTE_DISTS, K_TRUNCATE,
     K_ICP_BEGIN, K_ICP_L0, K_ICP_L1, K_ICP_L2, K_ICP_L3, K_POSE_UPDATE, K_POSE_SET,
     K_SET_TYPE3, K_MARK, K_ALLOC, K_VISIBLE_LIST, K_LIST_FLIP, K_INTEGRATE_BEGIN, K_INTEGRATE,
-    K_MINMAX_INIT, K_EXPECTED_DEPTHS, K_RAYCAST, K_ICP_MAPS, K_RESET_SCENE, K_ICP_ALL, K_RENDER_GREY, K_RAYCAST_SHARDED, K_APPLY_MARKS, K_MODEL_MAPS, K_PYR_MAPS, K_COUNT
+    K_MINMAX_INIT, K_EXPECTED_DEPTHS, K_RAYCAST, K_ICP_MAPS, K_RESET_SCENE, K_ICP_ALL, K_RENDER_GREY, K_RAYCAST_SHARDED, K_APPLY_MARKS, K_MODEL_MAPS, K_PYR_MAPS, K_SHARD_BARRIER, K_PUSH_FRAME, K_COUNT
 };
 constexpr int KT_MAX_EVENTS = 512;
 
@@ -72,6 +72,8 @@ struct DevState {
     unsigned long long voxel_updates;
     unsigned int list_ticket;   // CTAs of k_visible_list that are done; the last one flips the lists
     int int_cursor;             // next visible-list position k_integrate hands out
+    int shard_error;            // a cross-GPU barrier timed out
+    int pad2_[3];
 };
 
 // payload owner of a block when the scene is sharded (new; the reference is single-GPU).  A different mix than
@@ -90,6 +92,8 @@ struct ShardView {
     const unsigned int* vba[TFB_MAX_SHARDS];
     float4* raycast[TFB_MAX_SHARDS];
     unsigned int* marks[TFB_MAX_SHARDS];
+    uint16_t* frame[TFB_MAX_SHARDS];
+    unsigned int* flags[TFB_MAX_SHARDS];
 };
 
 struct LevelBuf {
@@ -171,6 +175,8 @@ struct tfb_ctx {
     tfb::ShardView* shard_dev; // device copy (kernels that take it by pointer)
     unsigned int attached;     // bit r set once rank r's buffers are attached
     unsigned int* marks;       // incoming visibility marks: [0] count, [1] pad, then 2 words per mark
+    unsigned int* sync_flags;  // TFB_MAX_SHARDS words: the barrier epochs the other ranks have published here
+    unsigned int sync_epoch;
     int frame_stage;           // 0 idle, 1 after tfb_frame_begin, 2 after tfb_frame_raycast
     bool frame_first;
     // software pipeline of the unsharded frame: preprocessing runs on stream_pre beside the deferred tail
@@ -252,6 +258,8 @@ int launch_render_grey(tfb_ctx* c, uchar4* out);
 int launch_raycast(tfb_ctx* c, bool update_visible);
 int launch_raycast_sharded(tfb_ctx* c, bool viewer);
 int launch_apply_marks(tfb_ctx* c);
+int launch_shard_barrier(tfb_ctx* c);
+int launch_shard_push_frame(tfb_ctx* c, const uint16_t* depth_dev);
 int launch_model_maps(tfb_ctx* c);
 
 }  // namespace tfb

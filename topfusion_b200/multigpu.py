@@ -21,6 +21,7 @@ from __future__ import annotations
 
 import json
 import os
+import sys
 import time
 
 import numpy as np
@@ -50,7 +51,10 @@ def rows_of_rank(rows: int, rank: int, count: int, strip: int = 8):
 class CudaEngine:
     """this rank's tfb context on its GPU, attached to every other rank's buffers through CUDA IPC"""
 
-    def __init__(self, rank: int, world: int, device_index: int, dist, group=None, **params):
+    def __init__(self, rank: int, world: int, device_index: int, dist, group=None, plumbing: str = "p2p", **params):
+        """plumbing: "p2p" — frame push and barriers are this library's own kernels over peer memory (tfb_shard_push_frame /
+        tfb_shard_barrier); "nccl" — torch.distributed broadcast and one-element all-reduces on the same stream."""
+        self.plumbing = plumbing if world > 1 else "none"
         import torch
         from . import capi
         self.capi, self.torch = capi, torch
@@ -76,7 +80,15 @@ class CudaEngine:
                 self.ctx.shard_attach(r, p)
 
     def begin(self, frame):
-        self.ctx.frame_begin(frame.data_ptr())   # device tensor, rows x cols u16 (viewed as int16 by torch)
+        # device tensor, rows x cols u16 (viewed as int16 by torch); with the p2p plumbing rank 0 has already pushed it into
+        # every rank's own frame buffer
+        self.ctx.frame_begin(None if self.plumbing == "p2p" else frame.data_ptr())
+
+    def push_frame(self, frame):
+        self.ctx.shard_push_frame(frame.data_ptr())
+
+    def barrier(self):
+        self.ctx.shard_barrier()
 
     def raycast(self):
         self.ctx.frame_raycast()
@@ -114,16 +126,30 @@ class ShardedTopFu:
         self._flag = torch.zeros(1, dtype=torch.int32, device=frame_buffer.device)
         self.frames_done = 0
 
+    def _own_plumbing(self) -> bool:
+        return getattr(self.engine, "plumbing", "") == "p2p"
+
     def barrier(self):
-        """cross-rank barrier ON THE STREAM: a one-element all-reduce (no host synchronisation with NCCL)"""
-        if self.world > 1:
+        """cross-rank barrier ON THE STREAM (no host synchronisation): the engine's own flag barrier over peer memory, or a
+        one-element all-reduce"""
+        if self.world <= 1:
+            return
+        if self._own_plumbing():
+            self.engine.barrier()
+        else:
             self.dist.all_reduce(self._flag, group=self.group)
 
     def distribute(self, frame_src=None):
         """rank 0 copies its frame into the buffer (H2D when it is a pinned host tensor), everyone receives it"""
         if self.rank == 0 and frame_src is not None:
             self.frame.copy_(frame_src, non_blocking=True)
-        if self.world > 1:
+        if self.world <= 1:
+            return
+        if self._own_plumbing():
+            if self.rank == 0:
+                self.engine.push_frame(self.frame)   # one kernel: NVLink stores into every rank's frame buffer
+            self.barrier()                            # the frame has arrived everywhere
+        else:
             self.dist.broadcast(self.frame.view(self.torch.uint8), src=0, group=self.group)   # bytes: every backend moves u8
 
     def process_frame(self, frame_src=None) -> bool:
@@ -144,6 +170,66 @@ class ShardedTopFu:
 
 
 # ---------------------------------------------------------------------------------------------------------
+# voxel-updates/s on the large scene (BASELINE.json configs[3]): the part of the path that shards with no exchange at all
+# ---------------------------------------------------------------------------------------------------------
+LARGE_SCENE = "S3 large scene (2x1x2 m room shell + 20 boxes), 640x480, 2 mm voxels, mu 16 mm, ground-truth poses"
+
+
+def integrate_scaling_leg(rank: int, world: int, reduce_max=None, reduce_sum=None, frames: int = 24, warm: int = 4):
+    """every rank allocates the replicated index and integrates the blocks it owns from the same frames; no collective on
+    the data path.  Returns aggregate voxel-updates/s = updates of all ranks / slowest rank's k_integrate time."""
+    import ctypes as C
+    from . import capi, synth
+    n_seq = 12
+    cache = os.path.join("/tmp", "tfb_s3_12.npz")
+    if os.path.exists(cache):
+        z = np.load(cache)
+        depth, poses = z["depth"], z["poses"]
+    else:
+        depth, poses, _ = synth.sequence("S3", n_seq)
+        if rank == 0:
+            try:
+                np.savez(cache, depth=depth, poses=poses)
+            except OSError:
+                pass
+    ctx = capi.Context(voxel_size=0.002, mu=0.016, num_blocks=1 << 19, num_buckets=1 << 22, excess_size=1 << 18,
+                       depth_cutoff_mm=4000, shard_rank=rank, shard_count=world)
+    dev = [ctx.upload(depth[i]) for i in range(n_seq)]
+    dists = capi.DevBuf(depth.shape[1] * depth.shape[2] * 4)
+    order, i, step = [], 0, 1
+    while len(order) < warm + frames:
+        order.append(i)
+        if i + step >= n_seq or i + step < 0:
+            step = -step
+        i += step
+    upd = 0
+    for t, fi in enumerate(order):
+        if t == warm:
+            ctx.ktiming(True)
+        w2c = np.ascontiguousarray(np.linalg.inv(poses[fi]), dtype=np.float32)
+        ctx._ck(ctx.L.tfb_compute_dists(ctx.h, dev[fi].ptr, dists.ptr, C.c_int(depth.shape[2]), C.c_int(depth.shape[1])))
+        ctx._ck(ctx.L.tfb_allocate_scene_from_depth(ctx.h, w2c.ctypes.data_as(C.c_void_p), dists.ptr))
+        ctx.flush_l2()
+        ctx._ck(ctx.L.tfb_integrate_into_scene(ctx.h, w2c.ctypes.data_as(C.c_void_p), dists.ptr))
+        if t >= warm:
+            upd += ctx.voxel_updates()
+    ms, launches = ctx.kernel_times()["k_integrate"]
+    ctx.close()
+    ms_max = reduce_max(ms) if reduce_max else ms
+    upd_all = reduce_sum(upd) if reduce_sum else upd
+    peak = 6542.7
+    try:
+        peak = float(json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    per_s = upd_all / (ms_max / 1000.0)
+    return {"workload": LARGE_SCENE, "value": per_s, "unit": "voxel-updates/s", "frames": frames,
+            "visible_blocks_per_frame_all_ranks": upd_all / 512.0 / frames, "k_integrate_us_slowest_rank": 1000.0 * ms_max / launches,
+            "algorithmic_gbs_all_ranks": per_s * 8.04 / 1e9, "frac_of_measured_hbm_peak_per_gpu": per_s * 8.04 / 1e9 / world / peak,
+            "l2": "flushed before every integration"}
+
+
+# ---------------------------------------------------------------------------------------------------------
 # bench.py --gpus N (launched by torchrun, one rank per GPU)
 # ---------------------------------------------------------------------------------------------------------
 def bench_main(args, rank, world, local_rank, orbit_frames, ClockSampler, workload):
@@ -151,6 +237,10 @@ def bench_main(args, rank, world, local_rank, orbit_frames, ClockSampler, worklo
     import torch.distributed as dist
     from . import capi
 
+    # stdout carries exactly one JSON line: NCCL and the launcher print there too, so park it on stderr until the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     os.environ.setdefault("MASTER_PORT", "29511")
     torch.cuda.set_device(local_rank)
@@ -162,7 +252,7 @@ def bench_main(args, rank, world, local_rank, orbit_frames, ClockSampler, worklo
     dev = torch.device("cuda", local_rank)
 
     def run(leg: str):
-        eng = CudaEngine(rank, world, local_rank, dist, corrected_mode=args.mode)
+        eng = CudaEngine(rank, world, local_rank, dist, plumbing=os.environ.get("TFB_PLUMBING", "p2p"), corrected_mode=args.mode)
         with torch.cuda.stream(eng.stream):
             buf = torch.empty((rows, cols), dtype=torch.int16, device=dev)
             st = ShardedTopFu(eng, dist, rank, world, buf)
@@ -203,6 +293,16 @@ def bench_main(args, rank, world, local_rank, orbit_frames, ClockSampler, worklo
     ms, vox, oks, launches, pose_err, n_alloc = run("resident")
     clocks = sampler.result()
     e_ms, _, _, _, _, _ = run("e2e")
+
+    def red(op):
+        def f(v):
+            t = torch.tensor([float(v)], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=op)
+            return float(t.item())
+        return f
+    large = integrate_scaling_leg(rank, world, red(dist.ReduceOp.MAX), red(dist.ReduceOp.SUM))
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
     if rank == 0:
         line = {
             "metric": "frames/sec (ICP+integrate+raycast, 640x480)", "value": K / (ms / 1000.0), "unit": "frames/s",
@@ -210,14 +310,21 @@ def bench_main(args, rank, world, local_rank, orbit_frames, ClockSampler, worklo
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload, "mode": "corrected" if args.mode else "reference", "voxel_size_m": 0.005,
                        "parallelism": f"scene sharded over {world} GPUs by block-coordinate hash: index replicated, "
-                                      "payload + integration + raycast rows partitioned, peer-memory raycast; ICP replicated",
+                                      "payload + integration + raycast rows partitioned, peer-memory raycast; ICP replicated; "
+                                      "frame push and barriers: " + os.environ.get("TFB_PLUMBING", "p2p"),
                        "l2": "256 MB scratch overwritten between timed steps (L2 flushed)",
                        "final_pose_err_m": pose_err, "frames_tracked": oks, "blocks_allocated_all_ranks": n_alloc},
             "e2e": {"value": K / (e_ms / 1000.0), "unit": "frames/s", "h2d_bytes_per_step": rows * cols * 2,
                     "d2h_bytes_per_step": 448, "ms_per_step": e_ms / K},
             "gpu_launches": launches, "clocks": clocks,
             "voxel_updates_per_s": vox / (ms / 1000.0),
-            "roofline": None, "cpu_baseline": None,
+            "voxel_updates_large_scene": large,
+            "roofline": {"bound": "hbm", "kernel": "k_integrate", "achieved": large["algorithmic_gbs_all_ranks"] / world,
+                         "peak": large["algorithmic_gbs_all_ranks"] / world / max(large["frac_of_measured_hbm_peak_per_gpu"], 1e-12),
+                         "unit": "GB/s", "frac": large["frac_of_measured_hbm_peak_per_gpu"], "traffic": None,
+                         "note": "per GPU, on the large-scene integration leg (the stage that shards without exchange); "
+                                 "the N=1 line carries the frame's dominant kernel"},
+            "cpu_baseline": None,
         }
         print(json.dumps(line))
     dist.barrier()
