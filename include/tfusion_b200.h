@@ -211,6 +211,17 @@ TFB_API int tfb_frame_raycast(tfb_ctx* c);
 TFB_API int tfb_frame_end(tfb_ctx* c, int* ok);
 TFB_API void* tfb_stream(tfb_ctx* c);   /* the cudaStream_t the context runs on */
 
+/* ---- getting the reconstruction out and back in (the step after the path) -------------------
+ * tfb_extract_points: surface points of the whole scene — zero crossings of the TSDF along the three voxel edges
+ * (both voxels observed, w > 0), linearly interpolated, world metres, float4 (x, y, z, 1).  The reference has only a stub
+ * (take_cloud, apps/demo.cpp:70-77) and a dormant per-pixel renderPointCloud_device (VisualisationHelper.hpp:150-198).
+ * *n_out = points found; min(*n_out, capacity) were written (call with capacity 0 to size the buffer).  Order is arbitrary. */
+TFB_API int tfb_extract_points(tfb_ctx* c, float* points_dev, int capacity, int* n_out);
+/* allocated blocks + pose history in one file; tfb_scene_load restores them into a context created with the same voxel
+ * size, band and hash geometry, rebuilds the visible list and the model maps for the last pose, and tracking goes on. */
+TFB_API int tfb_scene_save(tfb_ctx* c, const char* path);
+TFB_API int tfb_scene_load(tfb_ctx* c, const char* path);
+
 /* ---- inspection (tests, bench, debug dumps) ---------------------------------------------- */
 /* out[8] = n_visible, last_free_block, last_free_excess, n_new_this_frame, frame_counter, resets,
  *          n_raycast_extras, n_allocated */

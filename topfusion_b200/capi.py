@@ -96,6 +96,9 @@ def lib() -> C.CDLL:
             "tfb_ipc_close": [C.c_void_p],
             "tfb_frame_begin": [C.c_void_p, C.c_void_p],
             "tfb_frame_raycast": [C.c_void_p],
+            "tfb_extract_points": [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)],
+            "tfb_scene_save": [C.c_void_p, C.c_char_p],
+            "tfb_scene_load": [C.c_void_p, C.c_char_p],
             "tfb_shard_push_frame": [C.c_void_p, C.c_void_p],
             "tfb_shard_barrier": [C.c_void_p],
             "tfb_frame_end": [C.c_void_p, C.POINTER(C.c_int)],
@@ -320,6 +323,27 @@ class Context:
         p = _np_ptr(_f32(pose_c2w).reshape(16)) if pose_c2w is not None else None
         self._ck(self.L.tfb_render_image(self.h, p, out.ptr))
         return self.download(out, (self.rows, self.cols, 4), np.uint8)
+
+    # -- the reconstruction out and back in ------------------------------------------------------------------
+    def extract_points(self) -> np.ndarray:
+        """surface points of the whole scene, float32 [n, 4] (x, y, z, 1) in world metres, arbitrary order"""
+        n = C.c_int(0)
+        self._ck(self.L.tfb_extract_points(self.h, None, C.c_int(0), C.byref(n)))
+        if n.value == 0:
+            return np.zeros((0, 4), np.float32)
+        buf = DevBuf(n.value * 16)
+        m = C.c_int(0)
+        self._ck(self.L.tfb_extract_points(self.h, buf.ptr, C.c_int(n.value), C.byref(m)))
+        assert m.value == n.value
+        out = self.download(buf, (n.value, 4), np.float32)
+        buf.free()
+        return out
+
+    def save_scene(self, path: str):
+        self._ck(self.L.tfb_scene_save(self.h, path.encode()))
+
+    def load_scene(self, path: str):
+        self._ck(self.L.tfb_scene_load(self.h, path.encode()))
 
     # -- frames ----------------------------------------------------------------------------------------
     def process_frame(self, depth) -> bool:

@@ -251,6 +251,7 @@ int launch_pose_set(tfb_ctx* c, const float* pose_row_major_host, bool is_w2c);
 int launch_reset_scene(tfb_ctx* c);
 int launch_allocate(tfb_ctx* c, const float* dists);
 int launch_integrate(tfb_ctx* c, const float* dists);
+int launch_rebuild_visible(tfb_ctx* c);
 // vis
 int launch_expected_depths(tfb_ctx* c, bool reset_image = false);
 int launch_icp_maps(tfb_ctx* c, float4* points, float4* normals, bool do_raycast = true);
