@@ -423,7 +423,9 @@ int tfb_create(const tfb_params* p, void* stream, tfb_ctx** out) {
         }
     }
     c->icp_max_blocks = div_up(p->cols, 32) * div_up(p->rows, 8);
-    ok(dmalloc(&c->icp_partial, (size_t)64 * (c->icp_max_blocks > 1024 ? c->icp_max_blocks : 1024) + 64));
+    const size_t n_partial = (size_t)64 * (c->icp_max_blocks > 1024 ? c->icp_max_blocks : 1024) + 64;
+    ok(dmalloc(&c->icp_partial, n_partial));
+    if (e == cudaSuccess) cudaMemsetAsync(c->icp_partial, 0, n_partial * sizeof(float), c->stream);   // no stale epochs
     ok(cudaMalloc((void**)&c->ds, sizeof(DevState) + 64 * sizeof(float)));
     ok(cudaMalloc((void**)&c->marks, (size_t)(2 + 2 * MARKS_CAP) * sizeof(unsigned int)));
     ok(cudaMalloc((void**)&c->shard_dev, sizeof(ShardView)));

@@ -141,6 +141,7 @@ struct tfb_ctx {
     float* icp_partial;        // [ICP_TERMS][max_blocks]
     int icp_max_blocks;
     int icp_grid;              // persistent ICP grid (co-resident CTAs), sized on first use
+    unsigned int icp_launches; // epoch range of the partial rows, 64 per launch
     // state
     tfb::DevState* ds;         // device
     tfb::DevState* hs;         // pinned host mirror

@@ -426,8 +426,9 @@ __global__ void __launch_bounds__(ICP_THREADS)
 //   * persistent grid (one 512-thread CTA per SM, co-resident by cooperative launch), grid-stride over pixels with four
 //     independent pixels in flight per thread so the dependent load chain v -> (d, n_d) overlaps across pixels;
 //   * per iteration one CTA-level reduction (shuffles + shared memory), one row of partials per CTA, ONE grid
-//     barrier; then every CTA folds all partials in the same fixed order (fp64) and solves redundantly, which makes
-//     the result bit-identical in every CTA and saves the second barrier a broadcast would need;
+//     synchronisation point — the epoch-stamped rows themselves, polled by the fold; then every CTA folds all partials in the
+//     same fixed order (fp64) and solves redundantly, which makes the result bit-identical in every CTA and saves the
+//     second barrier a broadcast would need;
 //   * the last iteration composes poses_.back() * affine and derives the frame's matrices (topfu.cpp:243,281).
 // ---------------------------------------------------------------------------------------------------------
 struct IcpLevelArgs {
@@ -444,28 +445,14 @@ struct IcpAllArgs {
     int levels;
     float min_cosine, dist2_thres;
     int update_pose;
+    unsigned int epoch_base;   // this launch's range of row epochs (64 per launch)
 };
 
 constexpr int ICPA_THREADS = 512, ICPA_WARPS = ICPA_THREADS / 32, ICPA_UNROLL = 5;   // one CTA per SM
 
-// Grid barrier of the co-resident (cooperatively launched) CTAs.  Arrival is one release-reduction: it orders the CTA's
-// partial row (made visible to thread 0 by the bar.sync before it) ahead of the count.  The wait polls with relaxed
-// loads and deliberately issues NO acquire fence: on sm_100a an acquire (like __threadfence) is MEMBAR + CCTL.IVALL, which
-// throws away the SM's L1 — and with it the vertex / normal maps this CTA re-reads in every one of the 10/5/4 iterations
-// of a level.  Nothing read after the barrier can be stale in L1: the partial rows are read with L2-scope loads
-// (ld.relaxed.gpu), the maps are read-only for the whole kernel, the transform lives in shared memory.
-__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
-        unsigned int v;
-        do {
-            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-        } while (v < target);
-    }
-    __syncthreads();
-}
-
+// L2-scope load of a word of a partial row (rows are polled: they must never be served from a stale L1 line).  No acquire
+// fence is issued anywhere in the iteration loop: on sm_100a an acquire is MEMBAR + CCTL.IVALL, which throws away the SM's
+// L1 — and with it the vertex / normal maps this CTA re-reads in every one of the 10/5/4 iterations of a level.
 __device__ __forceinline__ float ld_partial(const float* p) {
     float v;
     asm volatile("ld.relaxed.gpu.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
@@ -474,7 +461,10 @@ __device__ __forceinline__ float ld_partial(const float* p) {
 
 #ifdef TFB_ICP_PROFILE
 __device__ long long g_icp_prof[64 * 8];
-#define ICP_STAMP(slot) do { if (blockIdx.x == 0 && tid == 0 && iter_global < 64) g_icp_prof[iter_global * 8 + (slot)] = clock64(); } while (0)
+__device__ long long g_icp_cta[256 * 4];   // iteration 12 (level 0): per CTA globaltimer at pixel start, pixel end, row stored, fold done
+#define ICP_STAMP(slot) do { if (blockIdx.x == 0 && tid == 0 && iter_global < 64) g_icp_prof[iter_global * 8 + (slot)] = clock64(); \
+    if (iter_global == 12 && tid == 0 && blockIdx.x < 256 && ((slot) == 0 || (slot) == 1 || (slot) == 2 || (slot) == 4)) { long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); \
+        g_icp_cta[blockIdx.x * 4 + ((slot) == 0 ? 0 : (slot) == 1 ? 1 : (slot) == 2 ? 2 : 3)] = gt; } } while (0)
 #else
 #define ICP_STAMP(slot) do { } while (0)
 #endif
@@ -544,7 +534,7 @@ __device__ __forceinline__ void icp_pixels(const IcpLevelArgs& L, const IcpAllAr
 }
 
 __global__ void __launch_bounds__(ICPA_THREADS, 1)
-    k_icp_all(IcpAllArgs a, DevState* __restrict__ ds, float* __restrict__ partial, unsigned int* __restrict__ barrier) {
+    k_icp_all(IcpAllArgs a, DevState* __restrict__ ds, float* __restrict__ partial) {
     __shared__ float s_warp[ICPA_WARPS][ICP_ACC];
     __shared__ double s_part[ICPA_WARPS][32];
     __shared__ double s_tot[ICP_ACC];
@@ -560,7 +550,6 @@ __global__ void __launch_bounds__(ICPA_THREADS, 1)
     if (tid == 0) s_ok = 1;
     __syncthreads();
 
-    unsigned int bar_target = 0;
     int iter_global = 0;
     bool ok = true;
     for (int l = a.levels - 1; l >= 0 && ok; --l) {
@@ -599,42 +588,57 @@ __global__ void __launch_bounds__(ICPA_THREADS, 1)
                 if (lane < ICP_ACC) s_warp[warp][lane] = v[0];
             }
             __syncthreads();
+            // The CTA's row of partials IS its barrier arrival: 128 bytes = four 32-byte sectors, each holding seven sums and,
+            // in its eighth word, the epoch of this iteration (unique across iterations and launches).  A sector is written
+            // and read as a unit, so a reader that sees the epoch in a sector sees that sector's sums — no fence, no counter,
+            // no second round trip: the fold below simply re-reads a row until its four epochs match.  Rows are double
+            // buffered by iteration parity; a CTA can only write iteration i+2 after every CTA has finished reading i.
+            const unsigned int epoch = a.epoch_base + (unsigned)iter_global + 1u;
             float* prow = partial + (size_t)(iter_global & 1) * nblk * 32;
             if (tid < 32) {
-                float sacc = 0.f;
-                if (tid < ICP_ACC) {
+                float val = __uint_as_float(epoch);
+                if ((tid & 7) != 7) {
+                    const int term = (tid >> 3) * 7 + (tid & 7);
+                    float sacc = 0.f;
 #pragma unroll
-                    for (int wi = 0; wi < ICPA_WARPS; ++wi) sacc += s_warp[wi][tid];
+                    for (int wi = 0; wi < ICPA_WARPS; ++wi) sacc += s_warp[wi][term];
+                    val = sacc;
                 }
-                prow[blockIdx.x * 32 + tid] = sacc;
+                asm volatile("st.relaxed.gpu.global.f32 [%0], %1;" ::"l"(prow + blockIdx.x * 32 + tid), "f"(val) : "memory");
             }
-            bar_target += (unsigned)nblk;
             ICP_STAMP(2);
-            grid_barrier(barrier, bar_target);
             ICP_STAMP(3);
 
-            // every CTA: fold all partials in the same order (fp64), solve, update its copy of the transform
+            // every CTA: fold all rows in the same order (fp64), solve, update its copy of the transform
             {
-                // warp p takes CTAs p, p+16, ...; all of a warp's loads are in flight before the first add
+                // warp p takes CTAs p, p+16, ...; lane = word of the row; all of a warp's loads are in flight before the first add
                 const int k = lane, part = warp;
+                const bool flag_lane = (k & 7) == 7;
                 double sd = 0;
                 for (int b0 = part; b0 < nblk; b0 += ICPA_WARPS * 10) {
                     float tmp[10];
 #pragma unroll
                     for (int j = 0; j < 10; ++j) {
                         const int b = b0 + j * ICPA_WARPS;
-                        tmp[j] = (b < nblk) ? ld_partial(prow + b * 32 + k) : 0.f;
+                        tmp[j] = (b < nblk) ? ld_partial(prow + b * 32 + k) : __uint_as_float(epoch);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 10; ++j) {
+                        const int b = b0 + j * ICPA_WARPS;
+                        while (__any_sync(0xffffffffu, flag_lane && __float_as_uint(tmp[j]) != epoch))   // row not there yet
+                            tmp[j] = ld_partial(prow + b * 32 + k);
                     }
 #pragma unroll
                     for (int j = 0; j < 10; ++j) sd += (double)tmp[j];
                 }
-                s_part[part][k] = sd;
+                s_part[part][k] = sd;   // the flag lanes sum nonsense; nobody reads them
             }
             __syncthreads();
             if (tid < ICP_ACC) {
+                const int word = (tid / 7) * 8 + (tid % 7);
                 double sd = 0;
 #pragma unroll
-                for (int p = 0; p < ICPA_WARPS; ++p) sd += s_part[p][tid];
+                for (int p = 0; p < ICPA_WARPS; ++p) sd += s_part[p][word];
                 s_tot[tid] = sd;
             }
             __syncthreads();
@@ -676,6 +680,9 @@ __global__ void __launch_bounds__(ICPA_THREADS, 1)
 }
 
 #ifdef TFB_ICP_PROFILE
+extern "C" __attribute__((visibility("default"))) int tfb_debug_icp_cta(long long* out1024) {
+    return cudaMemcpyFromSymbol(out1024, g_icp_cta, sizeof(long long) * 1024) == cudaSuccess ? 0 : -2;
+}
 extern "C" __attribute__((visibility("default"))) int tfb_debug_icp_profile(long long* out512) {
     return cudaMemcpyFromSymbol(out512, g_icp_prof, sizeof(long long) * 64 * 8) == cudaSuccess ? 0 : -2;
 }
@@ -736,11 +743,10 @@ static int launch_icp_args(tfb_ctx* c, IcpAllArgs& a, int total) {
         c->icp_grid = sms;   // one CTA per SM: the partial rows every CTA folds grow with the grid
         if (c->icp_grid > c->icp_max_blocks) c->icp_grid = c->icp_max_blocks;
     }
-    unsigned int* bar = &c->ds->icp_ticket;
-    TFB_CUDA(c, cudaMemsetAsync(bar, 0, sizeof(unsigned int), c->stream));
+    a.epoch_base = (unsigned int)(++c->icp_launches) * 64u;   // rows of earlier launches can never match
     DevState* ds = c->ds;
     float* partial = c->icp_partial;
-    void* args[] = {&a, &ds, &partial, &bar};
+    void* args[] = {&a, &ds, &partial};
     TFB_KT(c, K_ICP_ALL);
     TFB_CUDA(c, cudaLaunchCooperativeKernel((const void*)k_icp_all, dim3(c->icp_grid), dim3(ICPA_THREADS), args, 0, c->stream));
     TFB_LAUNCH_CHECK(c);
