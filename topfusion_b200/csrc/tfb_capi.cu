@@ -48,6 +48,8 @@ void free_all(tfb_ctx* c) {
             if (c->kt_ev[i]) cudaEventDestroy(c->kt_ev[i]);
         free(c->kt_ev);
     }
+    if (c->ev_alloc) cudaEventDestroy(c->ev_alloc);
+    if (c->ev_expect) cudaEventDestroy(c->ev_expect);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->ev_pre0) cudaEventDestroy(c->ev_pre0);
@@ -224,10 +226,22 @@ int enqueue_tail(tfb_ctx* c) {
     const float* dists = c->tail_dists;
     stamp(c, ST_ALLOC);
     if ((r = launch_allocate(c, dists))) return r;
+    // the expected-depth image needs the visible list and the pose, not the voxels: it runs beside the integration
+    TFB_CUDA(c, cudaEventRecord(c->ev_alloc, c->stream));
+    TFB_CUDA(c, cudaStreamWaitEvent(c->stream_pre, c->ev_alloc, 0));
+    {
+        cudaStream_t main_stream = c->stream;
+        c->stream = c->stream_pre;
+        r = launch_expected_depths(c);
+        cudaError_t e = cudaEventRecord(c->ev_expect, c->stream);
+        c->stream = main_stream;
+        if (r) return r;
+        if (e != cudaSuccess) return set_err(c, TFB_ERR_CUDA, "event record", e);
+    }
     stamp(c, ST_INTEG);
     if ((r = launch_integrate(c, dists))) return r;
     stamp(c, ST_EXPECT);
-    if ((r = launch_expected_depths(c))) return r;
+    TFB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_expect, 0));
     stamp(c, ST_RAYCAST);
     if ((r = launch_raycast(c, true))) return r;
     if ((r = launch_model_maps(c))) return r;
@@ -291,9 +305,33 @@ int do_frame(tfb_ctx* c, const uint16_t* depth, size_t host_step_bytes, int* ok)
         c->tail_dists = dists;
         if ((r = launch_allocate(c, dists))) return r;
         if ((r = launch_integrate(c, dists))) return r;
-    } else if ((r = do_icp(c, true))) return r;
-    stamp(c, ST_FRAME);
-    if ((r = fetch_state(c))) return r;   // the one wait of the call: pose, verdict, counters
+    }
+    // the one wait of the call: pose, verdict, counters.  Tracked frames: k_icp_all writes the state block into the pinned
+    // mirror itself and the host spins on the sequence word behind it; otherwise (frame 0, event timing on) a D2H copy.
+    const bool zero_copy = !first && !c->timing && !c->ktiming;
+    if (!first) {
+        c->publish_seq = zero_copy ? ++c->seq_counter : 0u;
+        if (c->publish_seq == 0u && zero_copy) c->publish_seq = ++c->seq_counter;   // skip 0 on wrap-around
+        r = do_icp(c, true);
+        const unsigned int want = c->publish_seq;
+        c->publish_seq = 0u;
+        if (r) return r;
+        stamp(c, ST_FRAME);
+        if (zero_copy) {
+            volatile unsigned int* seq = reinterpret_cast<volatile unsigned int*>(c->hs) + sizeof(DevState) / sizeof(unsigned int);
+            unsigned int spins = 0;
+            while (*seq != want) {
+                if ((++spins & 0xfffu) == 0u) {   // every few microseconds: has the stream died?
+                    cudaError_t q = cudaStreamQuery(c->stream);
+                    if (q != cudaSuccess && q != cudaErrorNotReady) return set_err(c, TFB_ERR_CUDA, "frame", q);
+                    if (q == cudaSuccess && *seq != want) return set_err(c, TFB_ERR_STATE, "ICP kernel finished without publishing its state");
+                }
+            }
+        }
+    } else {
+        stamp(c, ST_FRAME);
+    }
+    if (!zero_copy && (r = fetch_state(c))) return r;
     if (c->timing) {
         float t = 0.f;
         static const int seq[] = {ST_UPLOAD, ST_ALLOC, ST_INTEG, ST_EXPECT, ST_RAYCAST, ST_PYR, ST_ICP, ST_FRAME};
@@ -403,6 +441,8 @@ int tfb_create(const tfb_params* p, void* stream, tfb_ctx** out) {
     ok(cudaStreamCreateWithFlags(&c->stream_pre, cudaStreamNonBlocking));
     ok(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     ok(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    ok(cudaEventCreateWithFlags(&c->ev_alloc, cudaEventDisableTiming));
+    ok(cudaEventCreateWithFlags(&c->ev_expect, cudaEventDisableTiming));
     ok(cudaEventCreate(&c->ev_pre0));
     ok(cudaEventCreate(&c->ev_pre1));
     ok(dmalloc(&c->depth_in, npx));
@@ -430,7 +470,8 @@ int tfb_create(const tfb_params* p, void* stream, tfb_ctx** out) {
     ok(cudaMalloc((void**)&c->marks, (size_t)(2 + 2 * MARKS_CAP) * sizeof(unsigned int)));
     ok(cudaMalloc((void**)&c->shard_dev, sizeof(ShardView)));
     ok(cudaMalloc((void**)&c->sync_flags, TFB_MAX_SHARDS * sizeof(unsigned int)));
-    ok(cudaMallocHost((void**)&c->hs, sizeof(DevState)));
+    ok(cudaMallocHost((void**)&c->hs, sizeof(DevState) + 64));   // + the sequence word k_icp_all publishes behind the block
+    if (e == cudaSuccess) memset(c->hs, 0, sizeof(DevState) + 64);
     ok(cudaMallocHost((void**)&c->h_pose_stage, 64 * sizeof(float)));
     ok(cudaMallocHost((void**)&c->h_icp27, 32 * sizeof(float)));
     for (int i = 0; i < 16; ++i) ok(cudaEventCreate(&c->ev[i]));

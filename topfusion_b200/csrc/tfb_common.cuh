@@ -142,6 +142,8 @@ struct tfb_ctx {
     int icp_max_blocks;
     int icp_grid;              // persistent ICP grid (co-resident CTAs), sized on first use
     unsigned int icp_launches; // epoch range of the partial rows, 64 per launch
+    unsigned int publish_seq;  // != 0: k_icp_all writes the state block + this number into the pinned mirror (zero-copy)
+    unsigned int seq_counter;
     // state
     tfb::DevState* ds;         // device
     tfb::DevState* hs;         // pinned host mirror
@@ -182,7 +184,7 @@ struct tfb_ctx {
     bool frame_first;
     // software pipeline of the unsharded frame: preprocessing runs on stream_pre beside the deferred tail
     cudaStream_t stream_pre;
-    cudaEvent_t ev_fork, ev_join, ev_pre0, ev_pre1;
+    cudaEvent_t ev_fork, ev_join, ev_pre0, ev_pre1, ev_alloc, ev_expect;
     bool tail_pending;         // allocation .. model maps of the last tracked frame are still to be enqueued
     const float* tail_dists;
 };
