@@ -367,7 +367,7 @@ def main():
                    "l2": "256 MB scratch overwritten between timed steps (L2 flushed); warm-L2 figures given separately",
                    "visible_blocks_end": n_vis_end, "final_pose_err_m": pose_err, "frames_tracked": oks},
         "e2e": {"value": K / (e2e_ms / 1000.0), "unit": "frames/s", "h2d_bytes_per_step": rows * cols * 2,
-                "d2h_bytes_per_step": 448, "ms_per_step": e2e_ms / K, "warm_l2_value": K / (e2e_warm_ms / 1000.0)},
+                "d2h_bytes_per_step": 468, "ms_per_step": e2e_ms / K, "warm_l2_value": K / (e2e_warm_ms / 1000.0)},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": roof,

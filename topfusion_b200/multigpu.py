@@ -315,7 +315,7 @@ def bench_main(args, rank, world, local_rank, orbit_frames, ClockSampler, worklo
                        "l2": "256 MB scratch overwritten between timed steps (L2 flushed)",
                        "final_pose_err_m": pose_err, "frames_tracked": oks, "blocks_allocated_all_ranks": n_alloc},
             "e2e": {"value": K / (e_ms / 1000.0), "unit": "frames/s", "h2d_bytes_per_step": rows * cols * 2,
-                    "d2h_bytes_per_step": 448, "ms_per_step": e_ms / K},
+                    "d2h_bytes_per_step": 468, "ms_per_step": e_ms / K},
             "gpu_launches": launches, "clocks": clocks,
             "voxel_updates_per_s": vox / (ms / 1000.0),
             "voxel_updates_large_scene": large,
