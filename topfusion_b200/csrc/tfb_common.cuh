@@ -14,7 +14,7 @@ enum KernelId {
     K_BILATERAL = 0, K_DEPTH_PYR, K_POINTS_NORMALS, K_RESIZE_MAPS, K_COMPUTE_DISTS, K_TRUNCATE,
     K_ICP_BEGIN, K_ICP_L0, K_ICP_L1, K_ICP_L2, K_ICP_L3, K_POSE_UPDATE, K_POSE_SET,
     K_SET_TYPE3, K_MARK, K_ALLOC, K_VISIBLE_LIST, K_LIST_FLIP, K_INTEGRATE_BEGIN, K_INTEGRATE,
-    K_MINMAX_INIT, K_EXPECTED_DEPTHS, K_RAYCAST, K_ICP_MAPS, K_RESET_SCENE, K_ICP_ALL, K_RENDER_GREY, K_RAYCAST_SHARDED, K_APPLY_MARKS, K_MODEL_MAPS, K_PYR_MAPS, K_SHARD_BARRIER, K_PUSH_FRAME, K_COUNT
+    K_MINMAX_INIT, K_EXPECTED_DEPTHS, K_RAYCAST, K_ICP_MAPS, K_RESET_SCENE, K_ICP_ALL, K_RENDER_GREY, K_RAYCAST_SHARDED, K_APPLY_MARKS, K_MODEL_MAPS, K_PYR_MAPS, K_SHARD_BARRIER, K_PUSH_FRAME, K_COMPACT_OWNED, K_COUNT
 };
 constexpr int KT_MAX_EVENTS = 512;
 
@@ -73,7 +73,8 @@ struct DevState {
     unsigned int list_ticket;   // CTAs of k_visible_list that are done; the last one flips the lists
     int int_cursor;             // next visible-list position k_integrate hands out
     int shard_error;            // a cross-GPU barrier timed out
-    int pad2_[3];
+    int n_own;                  // sharded scene: entries of the visible list whose payload this rank holds
+    int pad2_[2];
 };
 
 // payload owner of a block when the scene is sharded (new; the reference is single-GPU).  A different mix than
@@ -130,6 +131,7 @@ struct tfb_ctx {
     // render state
     int* vis_type;             // per slot (reference: uchar entriesVisibleType)
     int* vis_list[2];          // double-buffered visibleEntryIDs; DevState::cur_list says which is current
+    int* own_list;             // sharded scene only: the visible entries this rank integrates (compacted each frame)
     float2* minmax;            // (rows/8) x (cols/8)
     float4* raycast;           // rows x cols
     // frames
