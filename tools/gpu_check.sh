@@ -12,5 +12,5 @@ $CMD > gpurun_out/plain_$TAG.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 300 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_l_$TAG.log 2>&1
 echo "ncu list rc=$?"
 $CMD > gpurun_out/plain_$TAG.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:"k_icp_all|k_integrate$|k_raycast|k_bilateral|k_mark" -s 10 -c 10 -f -o gpurun_out/prof_$TAG $CMD > gpurun_out/ncu_f_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"k_icp_all|k_integrate$|k_raycast|k_bilateral|k_mark|k_visible_list|k_model_maps|k_pyr_maps" -s 16 -c 16 -f -o gpurun_out/prof_$TAG $CMD > gpurun_out/ncu_f_$TAG.log 2>&1
 echo "ncu full rc=$?"

@@ -145,20 +145,25 @@ __device__ __forceinline__ void ldl6_f32(const float (&A)[36], Ldl6& f) {
     float d[6];
     f.ok = true;
     f.det = 1.0;
+    // this runs on ONE thread, 19 times per frame, on the critical path of every iteration: fused multiply-adds, the
+    // products l[j][k] * d[k] shared by the column below, and a Newton-refined MUFU reciprocal instead of a division
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
+        float ld[6];
         float dj = A[j * 6 + j];
 #pragma unroll
-        for (int k = 0; k < j; ++k) dj -= f.l[j][k] * f.l[j][k] * d[k];
+        for (int k = 0; k < j; ++k) { ld[k] = f.l[j][k] * d[k]; dj = __fmaf_rn(-f.l[j][k], ld[k], dj); }
         if (!(dj > tiny)) f.ok = false;
         d[j] = dj;
         f.det *= (double)dj;
-        f.dinv[j] = __fdiv_rn(1.0f, dj);
+        float y0;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(dj));
+        f.dinv[j] = __fmaf_rn(y0, __fmaf_rn(-dj, y0, 1.0f), y0);
 #pragma unroll
         for (int i = j + 1; i < 6; ++i) {
             float sacc = A[i * 6 + j];
 #pragma unroll
-            for (int k = 0; k < j; ++k) sacc -= f.l[i][k] * f.l[j][k] * d[k];
+            for (int k = 0; k < j; ++k) sacc = __fmaf_rn(-f.l[i][k], ld[k], sacc);
             f.l[i][j] = sacc * f.dinv[j];
         }
     }
@@ -171,14 +176,14 @@ __device__ __forceinline__ void ldl6_solve(const Ldl6& f, const T (&r)[6], float
     for (int i = 0; i < 6; ++i) {
         float v = (float)r[i];
 #pragma unroll
-        for (int k = 0; k < i; ++k) v -= f.l[i][k] * y[k];
+        for (int k = 0; k < i; ++k) v = __fmaf_rn(-f.l[i][k], y[k], v);
         y[i] = v;
     }
 #pragma unroll
     for (int i = 5; i >= 0; --i) {
         float v = y[i] * f.dinv[i];
 #pragma unroll
-        for (int k = i + 1; k < 6; ++k) v -= f.l[k][i] * x[k];
+        for (int k = i + 1; k < 6; ++k) v = __fmaf_rn(-f.l[k][i], x[k], v);
         x[i] = v;
     }
 }
