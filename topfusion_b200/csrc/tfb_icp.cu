@@ -548,7 +548,10 @@ __global__ void __launch_bounds__(ICPA_THREADS, 1)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nblk = gridDim.x;
-    const int gtid = blockIdx.x * ICPA_THREADS + tid;
+    // pixel slot of this thread: warps are dealt round-robin over the CTAs, so a CTA's 16 warps (x up to 5 pixel slots) sample
+    // the whole image instead of five contiguous runs of 512 pixels — the density of valid correspondences, and with it the
+    // length of the pixel phase, is then the same for every CTA (they all wait for the slowest one, 19 times a frame)
+    const int gtid = (warp * (int)gridDim.x + (int)blockIdx.x) * 32 + lane;
     const int gstride = nblk * ICPA_THREADS;
 
     if (tid < 16) s_aff[tid] = ((tid % 5) == 0) ? 1.f : 0.f;   // affine = Identity, projective_icp.cpp:174
@@ -622,16 +625,23 @@ __global__ void __launch_bounds__(ICPA_THREADS, 1)
                 double sd = 0;
                 for (int b0 = part; b0 < nblk; b0 += ICPA_WARPS * 10) {
                     float tmp[10];
+                    // poll: every round re-reads ALL rows that are still missing at once (one L2 round trip per round, not one
+                    // per late row), until the last of this warp's rows carries the epoch
+                    unsigned int pending = 0;
 #pragma unroll
                     for (int j = 0; j < 10; ++j) {
-                        const int b = b0 + j * ICPA_WARPS;
-                        tmp[j] = (b < nblk) ? ld_partial(prow + b * 32 + k) : __uint_as_float(epoch);
+                        tmp[j] = __uint_as_float(epoch);
+                        if (b0 + j * ICPA_WARPS < nblk) pending |= 1u << j;
                     }
+                    while (pending) {
 #pragma unroll
-                    for (int j = 0; j < 10; ++j) {
-                        const int b = b0 + j * ICPA_WARPS;
-                        while (__any_sync(0xffffffffu, flag_lane && __float_as_uint(tmp[j]) != epoch))   // row not there yet
-                            tmp[j] = ld_partial(prow + b * 32 + k);
+                        for (int j = 0; j < 10; ++j)
+                            if (pending & (1u << j)) tmp[j] = ld_partial(prow + (b0 + j * ICPA_WARPS) * 32 + k);
+                        unsigned int still = 0;
+#pragma unroll
+                        for (int j = 0; j < 10; ++j)
+                            if ((pending & (1u << j)) && __any_sync(0xffffffffu, flag_lane && __float_as_uint(tmp[j]) != epoch)) still |= 1u << j;
+                        pending = still;
                     }
 #pragma unroll
                     for (int j = 0; j < 10; ++j) sd += (double)tmp[j];
