@@ -67,6 +67,14 @@ struct TopFuApp {
         return true;
     }
 
+    // what demo.cpp's take_cloud stub (apps/demo.cpp:70-77) is there for: the reconstruction as a point cloud
+    void take_cloud() {
+        cuda::DeviceArray<float> cloud;
+        int n = 0;
+        topfu_->extractPoints(cloud, n);
+        std::printf("cloud: %d surface points\n", n);
+    }
+
     void save_view(const std::string& path) {
         if (view_host_.empty()) return;
         FILE* f = std::fopen(path.c_str(), "wb");
@@ -102,5 +110,6 @@ int main(int argc, char* argv[]) {
     TopFuApp app(corrected);
     bool ok = app.execute(argv[1], n);
     if (!out.empty()) app.save_view(out);
+    if (ok) app.take_cloud();
     return ok ? 0 : 1;
 }

@@ -63,6 +63,8 @@ struct KF_EXPORTS TopFuSceneConfig {
     bool corrected_mode = false;  // true: model maps are moved into the camera frame (fixes SURVEY.md F1)
     int shard_rank = 0, shard_count = 1;
     bool print_pose = false;      // the reference prints the pose every frame (topfu.cpp:252)
+    bool defer_tail = true;       // operator() returns once the pose is known; integration / raycast of that frame run beside the
+                                  // next frame's preprocessing (or before anything looks at the scene).  Results are identical.
 };
 
 class KF_EXPORTS TopFu {
@@ -90,6 +92,10 @@ public:
     // additions (not in the reference): the C context, for callers that want stage-level access or timings
     tfb_ctx* context() const { return ctx_; }
     long long voxelUpdatesLastFrame() const;
+    // the reconstruction as surface points (what apps/demo.cpp's take_cloud stub would fetch): x, y, z, 1 per point, world metres
+    void extractPoints(cuda::DeviceArray<float>& points4, int& count);
+    void saveScene(const std::string& path);
+    void loadScene(const std::string& path);
 
 private:
     TopFu(const TopFu&);

@@ -74,6 +74,7 @@ void TopFu::create(const TopFuSceneConfig& sc) {
     p.num_blocks = sc.num_blocks; p.num_buckets = sc.num_buckets; p.excess_size = sc.excess_size;
     p.depth_cutoff_mm = sc.depth_cutoff_mm; p.corrected_mode = sc.corrected_mode ? 1 : 0;
     p.shard_rank = sc.shard_rank; p.shard_count = sc.shard_count;
+    p.defer_tail = sc.defer_tail ? 1 : 0;
     int rc = tfb_create(&p, 0, &ctx_);
     if (rc != TFB_OK) cuda::error("tfb_create failed (no CUDA device, or out of memory)", __FILE__, __LINE__, "TopFu::TopFu");
 }
@@ -103,6 +104,20 @@ Affine3f TopFu::getCameraPose(int time) const {
 }
 
 long long TopFu::voxelUpdatesLastFrame() const { return tfb_voxel_updates_last(ctx_); }
+
+void TopFu::extractPoints(cuda::DeviceArray<float>& points4, int& count) {
+    int n = 0;
+    TF_CHECK(tfb_extract_points(ctx_, 0, 0, &n));
+    points4.create((size_t)(n > 0 ? n : 1) * 4);
+    TF_CHECK(tfb_extract_points(ctx_, points4.ptr(), n, &count));
+}
+
+void TopFu::saveScene(const std::string& path) { TF_CHECK(tfb_scene_save(ctx_, path.c_str())); }
+
+void TopFu::loadScene(const std::string& path) {
+    TF_CHECK(tfb_scene_load(ctx_, path.c_str()));
+    frame_counter_ = tfb_num_poses(ctx_);
+}
 
 bool TopFu::operator()(const cuda::Depth& depth, const cuda::Image&) {
     if (depth.rows() != params_.rows || depth.cols() != params_.cols)

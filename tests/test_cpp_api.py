@@ -64,6 +64,7 @@ def test_demo_synth_matches_the_c_abi_path(gpu, tmp_path):
             assert np.abs(t - g.pose()[:3, 3]).max() < 2e-5      # printed with 5 decimals
             assert int(rows[i][5]) == g.voxel_updates()
         img = g.render_image()
+        assert int(re.search(r"cloud: (\d+) surface points", r.stdout).group(1)) == g.extract_points().shape[0] > 50000
     finally:
         g.close()
     raw = open(view, "rb").read()
