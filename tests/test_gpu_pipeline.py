@@ -218,3 +218,24 @@ def test_deferred_tail_is_result_identical(gpu, s1_frames):
         assert np.array_equal(a.render_image(), b.render_image())
     finally:
         a.close(); b.close()
+
+
+def test_blank_first_frame_then_tracking(gpu, s1_frames):
+    """an empty first frame allocates nothing; the next frame cannot be tracked against an empty model -> reset, then the sequence
+    starts over.  Verdicts, pose counts and resets must follow the oracle."""
+    from oracle import tfo
+    depth, _, _ = s1_frames
+    o = tfo.Oracle(corrected_mode=1)
+    g = gpu.Context(corrected_mode=1)
+    try:
+        seq = [np.zeros_like(depth[0]), depth[0], depth[1], depth[2]]
+        for i, d in enumerate(seq):
+            ok_o, ok_g = o.process_frame(d), g.process_frame(d)
+            assert ok_o == ok_g, i
+            assert o.num_poses() == g.num_poses(), i
+            co, cg = o.counters(), g.counters()
+            assert co["resets"] == cg["resets"] and co["frame_counter"] == cg["frame_counter"], i
+            assert co["n_allocated"] == cg["n_allocated"], i
+        assert np.abs(o.pose()[:3, 3] - g.pose()[:3, 3]).max() < 1e-4
+    finally:
+        g.close(); o.close()

@@ -184,3 +184,30 @@ def test_viewer_render_bit_exact(both):
     assert (io[..., 0] > 0).mean() > 0.2
     assert np.array_equal(io, ig)
     assert np.array_equal(vis_before, g.vis_type()), "renderImage must not touch the visible set (updateVisibleList=false)"
+
+
+def test_ragged_depth_with_holes_and_noise_bit_exact(gpu, s1_frames):
+    """30 % of the pixels knocked out at random, 1 mm Gaussian noise on the rest: the block set, every voxel and every ray must
+    still match the oracle bit for bit (ragged segments, isolated pixels, blocks allocated from a single sample)"""
+    from oracle import tfo
+    depth, poses, _ = s1_frames
+    rng = np.random.RandomState(5)
+    noisy = []
+    for i in range(3):
+        d = depth[i].astype(np.float64)
+        d = np.where(d > 0, np.rint(d + rng.normal(0, 1.0, d.shape)), 0)
+        d[rng.rand(*d.shape) < 0.3] = 0
+        noisy.append(np.clip(d, 0, 65535).astype(np.uint16))
+    o, g, maps = _run_both(gpu, tfo, noisy, poses, 3)
+    try:
+        assert tfo.allocated_set(o.table()) == tfo.allocated_set(g.table())
+        assert tfo.visible_set(o.table(), o.visible_ids()) == tfo.visible_set(g.table(), g.visible_ids())
+        assert o.voxel_updates() == g.voxel_updates() > 0
+        bo, bg = o.blocks_by_pos(), g.blocks_by_pos()
+        for k in sorted(bo)[::3]:
+            assert np.array_equal(bo[k]["sdf"], bg[k]["sdf"]) and np.array_equal(bo[k]["w"], bg[k]["w"]), k
+        assert np.array_equal(o.raycast_result().view(np.uint32), g.raycast_result().view(np.uint32))
+        (op, on), (gp, gn) = maps[-1]
+        assert same_bits_nan(op, gp).all() and same_bits_nan(on, gn).all()
+    finally:
+        g.close(); o.close()
