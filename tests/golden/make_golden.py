@@ -2,7 +2,7 @@
 reference's OWN headers compiled where they lie under /root/reference (oracle/Makefile).  Runs only in the
 authoring container (the reference tree is not on the GPU box); the fixtures it writes are committed.
 
-    python tools/make_golden.py
+    python tests/golden/make_golden.py
 """
 import hashlib
 import os
@@ -10,7 +10,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import tfo  # noqa: E402
 from topfusion_b200 import synth  # noqa: E402

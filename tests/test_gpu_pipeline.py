@@ -177,7 +177,7 @@ def test_against_committed_golden_vectors(gpu):
                 po = z["est_poses"][i]
                 # 160x120 fixtures: this scene leaves directions of the 6x6 system almost unconstrained at that size
                 # (smallest eigenvalue 0.15 at level 2), so one correspondence flipping from a 1e-6 map difference
-                # moves the solution by millimetres (tools/diag_small2.py).  The north-star bound is asserted where the
+                # moves the solution by millimetres (seen with a 160x120 diagnostic run).  The north-star bound is asserted where the
                 # inputs are still bit-identical (frames 0-1) and on the full-resolution fixture throughout.
                 tight = cols >= 640 or i <= 1
                 tol_t, tol_r = (1e-4, 1e-4) if tight else (1.5e-2, 2e-2)

@@ -1,5 +1,5 @@
 """Oracle pinned to golden vectors.  The reference ships no tests or fixtures, so the
-vectors under tests/golden/ were produced by tools/make_golden.py from oracle/_ref — the build whose per-pixel /
+vectors under tests/golden/ were produced by tests/golden/make_golden.py from oracle/_ref — the build whose per-pixel /
 per-voxel functions are the reference's own headers compiled from /root/reference — and the oracle port must
 reproduce them bit for bit.  Runs on CPU."""
 import glob

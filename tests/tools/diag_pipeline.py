@@ -1,6 +1,6 @@
-"""diagnostic (GPU box): per-frame GPU-vs-oracle differences of the full pipeline"""
+"""TEST INFRASTRUCTURE (uses the oracle) — diagnostic (GPU box): per-frame GPU-vs-oracle differences of the full pipeline"""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from oracle import tfo
 from topfusion_b200 import capi, synth

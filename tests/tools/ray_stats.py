@@ -1,7 +1,7 @@
-"""CPU (oracle, test infrastructure): distribution of march lengths per ray and per 8x4 warp patch on the S1 orbit."""
+"""TEST INFRASTRUCTURE (uses the oracle) — CPU (oracle, test infrastructure): distribution of march lengths per ray and per 8x4 warp patch on the S1 orbit."""
 import ctypes as C, os, sys
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import tfo
 from topfusion_b200 import synth
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 8
