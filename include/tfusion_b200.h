@@ -204,6 +204,12 @@ TFB_API int tfb_ipc_close(void* dev_ptr);
  *                       single-process emulation orders the stages by stream order instead).  A rank that waits longer
  *                       than ~2 s gives up; the next tfb_frame_end reports TFB_ERR_STATE.
  * tfb_frame_begin(c, NULL) then tracks the frame in the context's frame buffer. */
+/* tfb_process_frame_sharded: the whole sharded frame in ONE call per rank — push (the rank that passes a frame, normally
+ * rank 0; the others pass NULL), barrier, then the software-pipelined frame of tfb_process_frame with the two remaining
+ * barriers inside the deferred tail.  *ok is operator()'s verdict, identical on every rank.  Collective: every rank calls it
+ * for every frame, in the same order; with defer_tail, so is every call that finishes a pending tail on a sharded context
+ * (tfb_sync, tfb_get_counters, the tfb_export_* family, tfb_render_image ...). */
+TFB_API int tfb_process_frame_sharded(tfb_ctx* c, const uint16_t* depth_dev_or_null, int* ok);
 TFB_API int tfb_shard_push_frame(tfb_ctx* c, const uint16_t* depth_dev);
 TFB_API int tfb_shard_barrier(tfb_ctx* c);
 TFB_API int tfb_frame_begin(tfb_ctx* c, const uint16_t* depth_dev);

@@ -31,6 +31,7 @@ def main():
         for i in range(n):
             src = torch.from_numpy(depth[i].view(np.int16)).pin_memory() if rank == 0 else None
             ok = st.process_frame(src)
+            eng.ctx.sync()                                   # collective: finishes the deferred tail on every rank
             upd = st.total(eng.voxel_updates())
             if rank == 0:
                 ok1 = single.process_frame(depth[i])

@@ -100,6 +100,7 @@ def lib() -> C.CDLL:
             "tfb_scene_save": [C.c_void_p, C.c_char_p],
             "tfb_scene_load": [C.c_void_p, C.c_char_p],
             "tfb_shard_push_frame": [C.c_void_p, C.c_void_p],
+            "tfb_process_frame_sharded": [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)],
             "tfb_shard_barrier": [C.c_void_p],
             "tfb_frame_end": [C.c_void_p, C.POINTER(C.c_int)],
         }.items():
@@ -380,6 +381,13 @@ class Context:
     def shard_push_frame(self, dev_ptr):
         p = dev_ptr.ptr if isinstance(dev_ptr, DevBuf) else C.c_void_p(dev_ptr)
         self._ck(self.L.tfb_shard_push_frame(self.h, p))
+
+    def process_frame_sharded(self, dev_ptr=None) -> bool:
+        """collective: the whole sharded frame; the rank that holds the frame passes it, the others None"""
+        ok = C.c_int(0)
+        p = None if dev_ptr is None else (dev_ptr.ptr if isinstance(dev_ptr, DevBuf) else C.c_void_p(dev_ptr))
+        self._ck(self.L.tfb_process_frame_sharded(self.h, p, C.byref(ok)))
+        return bool(ok.value)
 
     def shard_barrier(self):
         self._ck(self.L.tfb_shard_barrier(self.h))

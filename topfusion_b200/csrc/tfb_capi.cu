@@ -243,7 +243,13 @@ int enqueue_tail(tfb_ctx* c) {
     stamp(c, ST_EXPECT);
     TFB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_expect, 0));
     stamp(c, ST_RAYCAST);
-    if ((r = launch_raycast(c, true))) return r;
+    if (sharded(c)) {
+        // the collective frame (tfb_process_frame_sharded): every owner has integrated / every rank's rows have arrived
+        if ((r = launch_shard_barrier(c))) return r;
+        if ((r = launch_raycast_sharded(c, false))) return r;
+        if ((r = launch_shard_barrier(c))) return r;
+        if ((r = launch_apply_marks(c))) return r;
+    } else if ((r = launch_raycast(c, true))) return r;
     if ((r = launch_model_maps(c))) return r;
     stamp(c, ST_PYR);
     return TFB_OK;
@@ -265,9 +271,9 @@ int settle(tfb_ctx* c) {
 //     second stream [upload + preprocessing of this frame] -------------------------------------------------^
 // The reference runs the same stages strictly in sequence (topfu.cpp:161-330); the tail of frame k and the preprocessing
 // of frame k+1 are independent, and both leave most of the machine idle, so they share it.  Results are identical.
-int do_frame(tfb_ctx* c, const uint16_t* depth, size_t host_step_bytes, int* ok) {
-    if (sharded(c))
-        return set_err(c, TFB_ERR_STATE, "sharded context: drive the frame with tfb_frame_begin / _raycast / _end and a barrier between them");
+int do_frame(tfb_ctx* c, const uint16_t* depth, size_t host_step_bytes, int* ok, bool collective = false) {
+    if (sharded(c) && !collective)
+        return set_err(c, TFB_ERR_STATE, "sharded context: use tfb_process_frame_sharded, or tfb_frame_begin / _raycast / _end with a barrier between them");
     if (c->frame_stage != 0) return set_err(c, TFB_ERR_STATE, "a staged frame is in progress (tfb_frame_end)");
     int r;
     const bool first = (c->frame_counter == 0);
@@ -795,6 +801,21 @@ int tfb_shard_push_frame(tfb_ctx* c, const uint16_t* depth_dev) {
     if (c->attached != (1u << c->p.shard_count) - 1u) return set_err(c, TFB_ERR_STATE, "attach every rank's buffers first (tfb_shard_attach)");
     return launch_shard_push_frame(c, depth_dev);
 }
+// The whole sharded frame in one call per rank, software-pipelined like the single-GPU frame (the tail of the previous frame —
+// with its two cross-GPU barriers — beside this frame's preprocessing), on the library's own peer-memory plumbing.
+int tfb_process_frame_sharded(tfb_ctx* c, const uint16_t* depth_dev_or_null, int* ok) {
+    if (!c || !ok) return TFB_ERR_ARG;
+    if (c->p.shard_count > 1 && c->attached != (1u << c->p.shard_count) - 1u)
+        return set_err(c, TFB_ERR_STATE, "attach every rank's buffers first (tfb_shard_attach)");
+    if (c->p.shard_count <= 1) return depth_dev_or_null ? do_frame(c, depth_dev_or_null, 0, ok) : TFB_ERR_ARG;
+    int r;
+    if (depth_dev_or_null && (r = launch_shard_push_frame(c, depth_dev_or_null))) return r;
+    if ((r = launch_shard_barrier(c))) return r;   // the frame has arrived in every rank's frame buffer
+    r = do_frame(c, c->depth_in, 0, ok, true);
+    if (r == TFB_OK && c->hs->shard_error) return set_err(c, TFB_ERR_STATE, "a cross-GPU barrier timed out: another rank stopped");
+    return r;
+}
+
 int tfb_shard_barrier(tfb_ctx* c) {
     if (!c) return TFB_ERR_ARG;
     if (c->attached != (1u << c->p.shard_count) - 1u) return set_err(c, TFB_ERR_STATE, "attach every rank's buffers first (tfb_shard_attach)");

@@ -84,6 +84,10 @@ class CudaEngine:
         # every rank's own frame buffer
         self.ctx.frame_begin(None if self.plumbing == "p2p" else frame.data_ptr())
 
+    def process_collective(self, frame_or_none) -> bool:
+        """p2p plumbing: push + barriers + the software-pipelined frame in one library call (tfb_process_frame_sharded)"""
+        return self.ctx.process_frame_sharded(None if frame_or_none is None else frame_or_none.data_ptr())
+
     def push_frame(self, frame):
         self.ctx.shard_push_frame(frame.data_ptr())
 
@@ -125,6 +129,8 @@ class ShardedTopFu:
         self.frame = frame_buffer
         self._flag = torch.zeros(1, dtype=torch.int32, device=frame_buffer.device)
         self.frames_done = 0
+        # TFB_SHARD_PIPELINE=0: the three stages as separate calls with a barrier in between (what the NCCL plumbing needs)
+        self.pipelined = os.environ.get("TFB_SHARD_PIPELINE", "1") != "0"
 
     def _own_plumbing(self) -> bool:
         return getattr(self.engine, "plumbing", "") == "p2p"
@@ -153,6 +159,12 @@ class ShardedTopFu:
             self.dist.broadcast(self.frame.view(self.torch.uint8), src=0, group=self.group)   # bytes: every backend moves u8
 
     def process_frame(self, frame_src=None) -> bool:
+        if self.world > 1 and self._own_plumbing() and self.pipelined and hasattr(self.engine, "process_collective"):
+            if self.rank == 0 and frame_src is not None:
+                self.frame.copy_(frame_src, non_blocking=True)
+            ok = self.engine.process_collective(self.frame if self.rank == 0 else None)
+            self.frames_done += 1
+            return ok
         self.distribute(frame_src)
         self.engine.begin(self.frame)
         self.barrier()        # every owner has integrated: voxels are final
@@ -275,10 +287,12 @@ def bench_main(args, rank, world, local_rank, orbit_frames, ClockSampler, worklo
                 ok = st.process_frame(src[i] if rank == 0 else None)
                 if leg == "e2e":
                     _ = eng.pose()
+                if i == W:
+                    vox = -eng.ctx.voxel_updates_total()
                 if i >= W:
                     ev[i - W][1].record(eng.stream)
-                    vox += eng.voxel_updates()
                     oks += int(ok)
+            vox += eng.ctx.voxel_updates_total()   # integrations finished by the timed calls (host counter, does not wait)
             dist.barrier()
             torch.cuda.synchronize()
             ms = sum(a.elapsed_time(b) for a, b in ev)
