@@ -36,19 +36,34 @@ sys.path.insert(0, ROOT)
 WORKLOAD = "S1 synthetic 640x480 orbit (sphere+box+floor, 0.5 deg/frame), 5 mm voxels, mu 20 mm, ICP {10,5,4} on 3 levels"
 
 
+def _load_cache(path, keys):
+    """a cache file another rank may be writing right now is simply not used"""
+    try:
+        z = np.load(path)
+        return [z[k] for k in keys]
+    except Exception:
+        return None
+
+
+def _save_cache(path, **arrays):
+    tmp = f"{path}.{os.getpid()}.tmp.npz"
+    try:
+        np.savez(tmp, **arrays)
+        os.replace(tmp, path)      # atomic: readers see the old state or the complete file
+    except OSError:
+        pass
+
+
 def orbit_frames(n: int):
     """n consecutive frames of the 100-frame orbit; longer runs sweep back and forth so motion stays 0.5 deg/frame"""
     from topfusion_b200 import synth
     cache = os.path.join("/tmp", "tfb_s1_100.npz")
-    if os.path.exists(cache):
-        z = np.load(cache)
-        depth, poses = z["depth"], z["poses"]
+    got = _load_cache(cache, ("depth", "poses")) if os.path.exists(cache) else None
+    if got is not None:
+        depth, poses = got
     else:
         depth, poses, _ = synth.sequence("S1", 100)
-        try:
-            np.savez(cache, depth=depth, poses=poses)
-        except OSError:
-            pass
+        _save_cache(cache, depth=depth, poses=poses)
     idx = []
     i, step = 0, 1
     while len(idx) < n:
@@ -63,13 +78,11 @@ def seq_frames(name: str, n: int):
     """n frames of a synthetic sequence (cached under /tmp: the renderer costs ~0.1 s per frame)"""
     from topfusion_b200 import synth
     cache = os.path.join("/tmp", f"tfb_{name.lower()}_{n}.npz")
-    if os.path.exists(cache):
-        return np.load(cache)["depth"]
+    got = _load_cache(cache, ("depth",)) if os.path.exists(cache) else None
+    if got is not None:
+        return got[0]
     depth, _, _ = synth.sequence(name, n)
-    try:
-        np.savez(cache, depth=depth)
-    except OSError:
-        pass
+    _save_cache(cache, depth=depth)
     return depth
 
 

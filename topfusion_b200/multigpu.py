@@ -194,14 +194,20 @@ def integrate_scaling_leg(rank: int, world: int, reduce_max=None, reduce_sum=Non
     from . import capi, synth
     n_seq = 12
     cache = os.path.join("/tmp", "tfb_s3_12.npz")
+    depth = poses = None
     if os.path.exists(cache):
-        z = np.load(cache)
-        depth, poses = z["depth"], z["poses"]
-    else:
+        try:
+            z = np.load(cache)
+            depth, poses = z["depth"], z["poses"]
+        except Exception:      # another rank is writing it right now
+            depth = None
+    if depth is None:
         depth, poses, _ = synth.sequence("S3", n_seq)
         if rank == 0:
+            tmp = f"{cache}.{os.getpid()}.tmp.npz"
             try:
-                np.savez(cache, depth=depth, poses=poses)
+                np.savez(tmp, depth=depth, poses=poses)
+                os.replace(tmp, cache)
             except OSError:
                 pass
     ctx = capi.Context(voxel_size=0.002, mu=0.016, num_blocks=1 << 19, num_buckets=1 << 22, excess_size=1 << 18,
