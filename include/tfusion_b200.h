@@ -202,7 +202,7 @@ TFB_API int tfb_ipc_close(void* dev_ptr);
  *                       release stores and waits until every rank has published it.  Real multi-GPU only: the ranks'
  *                       kernels wait on one another, so every rank must own a GPU (never two ranks on one device — the
  *                       single-process emulation orders the stages by stream order instead).  A rank that waits longer
- *                       than ~2 s gives up; the next tfb_frame_end reports TFB_ERR_STATE.
+ *                       than ~10 s gives up; the frame then reports TFB_ERR_STATE.
  * tfb_frame_begin(c, NULL) then tracks the frame in the context's frame buffer. */
 /* tfb_process_frame_sharded: the whole sharded frame in ONE call per rank — push (the rank that passes a frame, normally
  * rank 0; the others pass NULL), barrier, then the software-pipelined frame of tfb_process_frame with the two remaining
