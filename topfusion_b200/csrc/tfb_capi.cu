@@ -30,7 +30,7 @@ cudaError_t dmalloc(T** p, size_t n) { return cudaMalloc((void**)p, n * sizeof(T
 
 void free_all(tfb_ctx* c) {
     cudaFree(c->table); cudaFree(c->vba); cudaFree(c->vba_free); cudaFree(c->excess_free);
-    cudaFree(c->claim_key); cudaFree(c->claimed); cudaFree(c->bucket_bits); cudaFree(c->vis_type); cudaFree(c->vis_list[0]); cudaFree(c->vis_list[1]); cudaFree(c->own_list);
+    cudaFree(c->claim_key); cudaFree(c->claimed); cudaFree(c->bucket_bits); cudaFree(c->vis_type); cudaFree(c->vis_list[0]); cudaFree(c->vis_list[1]); cudaFree(c->own_list); cudaFree(c->cache_pool); cudaFree(c->cache_tag);
     cudaFree(c->minmax); cudaFree(c->raycast); cudaFree(c->dists_buf[0]); cudaFree(c->dists_buf[1]); cudaFree(c->depth_in); cudaFree(c->icp_partial);
     cudaFree(c->ds); cudaFree(c->l2_scratch); cudaFree(c->marks); cudaFree(c->shard_dev); cudaFree(c->sync_flags);
     for (int l = 0; l < MAX_LEVELS; ++l) {
@@ -100,6 +100,7 @@ int do_reset(tfb_ctx* c) {
     if (r) return r;
     r = launch_reset_scene(c);
     if (r) return r;
+    c->shard.cache_epoch = ++c->gather_epoch;   // sharded scene: no copy of a foreign block outlives the scene
     return launch_pose_set(c, IDENTITY, false);
 }
 
@@ -164,6 +165,7 @@ int frame_raycast(tfb_ctx* c) {
         if (sharded(c)) {
             if (c->attached != (1u << c->p.shard_count) - 1u)
                 return set_err(c, TFB_ERR_STATE, "sharded context: attach every rank's buffers first (tfb_shard_attach)");
+            if ((r = launch_gather_foreign(c))) return r;
             if ((r = launch_raycast_sharded(c, false))) return r;
         } else if ((r = launch_raycast(c, true))) return r;
     } else {
@@ -246,6 +248,7 @@ int enqueue_tail(tfb_ctx* c) {
     if (sharded(c)) {
         // the collective frame (tfb_process_frame_sharded): every owner has integrated / every rank's rows have arrived
         if ((r = launch_shard_barrier(c))) return r;
+        if ((r = launch_gather_foreign(c))) return r;
         if ((r = launch_raycast_sharded(c, false))) return r;
         if ((r = launch_shard_barrier(c))) return r;
         if ((r = launch_apply_marks(c))) return r;
@@ -439,7 +442,16 @@ int tfb_create(const tfb_params* p, void* stream, tfb_ctx** out) {
     ok(dmalloc(&c->vis_type, (size_t)c->total_entries));
     ok(dmalloc(&c->vis_list[0], (size_t)c->total_entries));
     ok(dmalloc(&c->vis_list[1], (size_t)c->total_entries));
-    if (p->shard_count > 1) ok(dmalloc(&c->own_list, (size_t)c->total_entries));
+    if (p->shard_count > 1) {
+        ok(dmalloc(&c->own_list, (size_t)c->total_entries));
+        // room for the foreign blocks ONE frame sees (256 MB at most), not for the scene: what does not fit is read from its owner
+        const int cache_cap = p->num_blocks < (1 << 17) ? p->num_blocks : (1 << 17);
+        ok(dmalloc(&c->cache_pool, (size_t)cache_cap * BLOCK3));
+        ok(dmalloc(&c->cache_tag, (size_t)c->total_entries));
+        if (e == cudaSuccess) cudaMemsetAsync(c->cache_tag, 0, (size_t)c->total_entries * sizeof(unsigned long long), c->stream);
+        c->shard.cache_pool = c->cache_pool; c->shard.cache_tag = c->cache_tag; c->shard.cache_cap = cache_cap;
+        c->shard.cache_epoch = c->gather_epoch = 1u;   // the zeroed tags carry epoch 0: no copy yet
+    }
     ok(dmalloc(&c->minmax, npx / (MINMAX_SUB * MINMAX_SUB)));
     ok(dmalloc(&c->raycast, npx));
     ok(dmalloc(&c->dists_buf[0], npx));
@@ -960,7 +972,7 @@ static const char* const KNAMES[K_COUNT] = {
     "k_icp_begin", "k_icp_iteration[L0]", "k_icp_iteration[L1]", "k_icp_iteration[L2]", "k_icp_iteration[L3]", "(unused)",
     "k_pose_set", "k_set_type3", "k_mark", "k_alloc", "k_visible_list", "k_list_flip", "k_integrate_begin", "k_integrate",
     "k_minmax_init", "k_expected_depths", "k_raycast", "k_icp_maps", "k_reset_scene", "k_icp_all", "k_render_grey",
-    "k_raycast_sharded", "k_apply_marks", "k_model_maps", "k_pyramid_maps", "k_shard_barrier", "k_push_frame", "k_compact_owned"};
+    "k_raycast_sharded", "k_apply_marks", "k_model_maps", "k_pyramid_maps", "k_shard_barrier", "k_push_frame", "k_compact_owned", "k_gather_foreign"};
 
 int tfb_ktiming_enable(tfb_ctx* c, int on) {
     if (!c) return TFB_ERR_ARG;

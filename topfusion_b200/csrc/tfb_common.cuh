@@ -14,7 +14,7 @@ enum KernelId {
     K_BILATERAL = 0, K_DEPTH_PYR, K_POINTS_NORMALS, K_RESIZE_MAPS, K_COMPUTE_DISTS, K_TRUNCATE,
     K_ICP_BEGIN, K_ICP_L0, K_ICP_L1, K_ICP_L2, K_ICP_L3, K_POSE_UPDATE, K_POSE_SET,
     K_SET_TYPE3, K_MARK, K_ALLOC, K_VISIBLE_LIST, K_LIST_FLIP, K_INTEGRATE_BEGIN, K_INTEGRATE,
-    K_MINMAX_INIT, K_EXPECTED_DEPTHS, K_RAYCAST, K_ICP_MAPS, K_RESET_SCENE, K_ICP_ALL, K_RENDER_GREY, K_RAYCAST_SHARDED, K_APPLY_MARKS, K_MODEL_MAPS, K_PYR_MAPS, K_SHARD_BARRIER, K_PUSH_FRAME, K_COMPACT_OWNED, K_COUNT
+    K_MINMAX_INIT, K_EXPECTED_DEPTHS, K_RAYCAST, K_ICP_MAPS, K_RESET_SCENE, K_ICP_ALL, K_RENDER_GREY, K_RAYCAST_SHARDED, K_APPLY_MARKS, K_MODEL_MAPS, K_PYR_MAPS, K_SHARD_BARRIER, K_PUSH_FRAME, K_COMPACT_OWNED, K_GATHER_FOREIGN, K_COUNT
 };
 constexpr int KT_MAX_EVENTS = 512;
 
@@ -74,7 +74,8 @@ struct DevState {
     int int_cursor;             // next visible-list position k_integrate hands out
     int shard_error;            // a cross-GPU barrier timed out
     int n_own;                  // sharded scene: entries of the visible list whose payload this rank holds
-    int pad2_[2];
+    int n_cached;               // sharded scene: foreign visible blocks copied into the local cache this frame
+    int pad2_[1];
 };
 
 // payload owner of a block when the scene is sharded (new; the reference is single-GPU).  A different mix than
@@ -88,7 +89,11 @@ __host__ __device__ __forceinline__ int owner_rank(int bx, int by, int bz, int c
 
 // what a rank needs of every rank (itself included) to cast rays through a sharded scene: kernel parameter, by value
 struct ShardView {
-    int rank, count, marks_cap, pad_;
+    int rank, count, marks_cap, cache_cap;
+    // local copies of the foreign visible blocks of this frame (k_gather_foreign): tag[slot] = epoch << 32 | cache index
+    const unsigned int* cache_pool;
+    const unsigned long long* cache_tag;
+    unsigned int cache_epoch, pad_;
     const int4* table[TFB_MAX_SHARDS];
     const unsigned int* vba[TFB_MAX_SHARDS];
     float4* raycast[TFB_MAX_SHARDS];
@@ -180,8 +185,11 @@ struct tfb_ctx {
     tfb::ShardView* shard_dev; // device copy (kernels that take it by pointer)
     unsigned int attached;     // bit r set once rank r's buffers are attached
     unsigned int* marks;       // incoming visibility marks: [0] count, [1] pad, then 2 words per mark
+    unsigned int* cache_pool;        // sharded scene: this frame's copies of the foreign visible blocks (2 KB each)
+    unsigned long long* cache_tag;   // per hash slot: epoch << 32 | index into cache_pool
     unsigned int* sync_flags;  // TFB_MAX_SHARDS words: the barrier epochs the other ranks have published here
     unsigned int sync_epoch;
+    unsigned int gather_epoch;
     int frame_stage;           // 0 idle, 1 after tfb_frame_begin, 2 after tfb_frame_raycast
     bool frame_first;
     // software pipeline of the unsharded frame: preprocessing runs on stream_pre beside the deferred tail
@@ -265,6 +273,7 @@ int launch_raycast(tfb_ctx* c, bool update_visible);
 int launch_raycast_sharded(tfb_ctx* c, bool viewer);
 int launch_apply_marks(tfb_ctx* c);
 int launch_shard_barrier(tfb_ctx* c);
+int launch_gather_foreign(tfb_ctx* c);
 int launch_shard_push_frame(tfb_ctx* c, const uint16_t* depth_dev);
 int launch_model_maps(tfb_ctx* c);
 
