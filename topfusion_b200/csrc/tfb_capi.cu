@@ -100,7 +100,7 @@ int do_reset(tfb_ctx* c) {
     if (r) return r;
     r = launch_reset_scene(c);
     if (r) return r;
-    c->shard.cache_epoch = ++c->gather_epoch;   // sharded scene: no copy of a foreign block outlives the scene
+    next_cache_epoch(c);   // sharded scene: no copy of a foreign block outlives the scene
     return launch_pose_set(c, IDENTITY, false);
 }
 
@@ -182,7 +182,6 @@ int frame_end(tfb_ctx* c, int* ok) {
     int r;
     const bool first = c->frame_first;
     if (!first) {
-        if (sharded(c) && (r = launch_apply_marks(c))) return r;
         if ((r = launch_model_maps(c))) return r;
         stamp(c, ST_PYR);
     } else {
@@ -251,7 +250,6 @@ int enqueue_tail(tfb_ctx* c) {
         if ((r = launch_gather_foreign(c))) return r;
         if ((r = launch_raycast_sharded(c, false))) return r;
         if ((r = launch_shard_barrier(c))) return r;
-        if ((r = launch_apply_marks(c))) return r;
     } else if ((r = launch_raycast(c, true))) return r;
     if ((r = launch_model_maps(c))) return r;
     stamp(c, ST_PYR);
@@ -972,7 +970,7 @@ static const char* const KNAMES[K_COUNT] = {
     "k_icp_begin", "k_icp_iteration[L0]", "k_icp_iteration[L1]", "k_icp_iteration[L2]", "k_icp_iteration[L3]", "(unused)",
     "k_pose_set", "k_set_type3", "k_mark", "k_alloc", "k_visible_list", "k_list_flip", "k_integrate_begin", "k_integrate",
     "k_minmax_init", "k_expected_depths", "k_raycast", "k_icp_maps", "k_reset_scene", "k_icp_all", "k_render_grey",
-    "k_raycast_sharded", "k_apply_marks", "k_model_maps", "k_pyramid_maps", "k_shard_barrier", "k_push_frame", "k_compact_owned", "k_gather_foreign"};
+    "k_raycast_sharded", "k_model_maps", "k_pyramid_maps", "k_shard_barrier", "k_push_frame", "k_compact_owned", "k_gather_foreign"};
 
 int tfb_ktiming_enable(tfb_ctx* c, int on) {
     if (!c) return TFB_ERR_ARG;

@@ -14,7 +14,7 @@ enum KernelId {
     K_BILATERAL = 0, K_DEPTH_PYR, K_POINTS_NORMALS, K_RESIZE_MAPS, K_COMPUTE_DISTS, K_TRUNCATE,
     K_ICP_BEGIN, K_ICP_L0, K_ICP_L1, K_ICP_L2, K_ICP_L3, K_POSE_UPDATE, K_POSE_SET,
     K_SET_TYPE3, K_MARK, K_ALLOC, K_VISIBLE_LIST, K_LIST_FLIP, K_INTEGRATE_BEGIN, K_INTEGRATE,
-    K_MINMAX_INIT, K_EXPECTED_DEPTHS, K_RAYCAST, K_ICP_MAPS, K_RESET_SCENE, K_ICP_ALL, K_RENDER_GREY, K_RAYCAST_SHARDED, K_APPLY_MARKS, K_MODEL_MAPS, K_PYR_MAPS, K_SHARD_BARRIER, K_PUSH_FRAME, K_COMPACT_OWNED, K_GATHER_FOREIGN, K_COUNT
+    K_MINMAX_INIT, K_EXPECTED_DEPTHS, K_RAYCAST, K_ICP_MAPS, K_RESET_SCENE, K_ICP_ALL, K_RENDER_GREY, K_RAYCAST_SHARDED, K_MODEL_MAPS, K_PYR_MAPS, K_SHARD_BARRIER, K_PUSH_FRAME, K_COMPACT_OWNED, K_GATHER_FOREIGN, K_COUNT
 };
 constexpr int KT_MAX_EVENTS = 512;
 
@@ -271,9 +271,18 @@ int launch_icp_maps(tfb_ctx* c, float4* points, float4* normals, bool do_raycast
 int launch_render_grey(tfb_ctx* c, uchar4* out);
 int launch_raycast(tfb_ctx* c, bool update_visible);
 int launch_raycast_sharded(tfb_ctx* c, bool viewer);
-int launch_apply_marks(tfb_ctx* c);
 int launch_shard_barrier(tfb_ctx* c);
 int launch_gather_foreign(tfb_ctx* c);
+// Sharded scene: a new generation of the foreign-block cache (after anything that changes voxels, and for every gather).
+// 0 is the generation of the zeroed tags and 1 the one the device-resident ShardView carries: neither is ever handed out.
+inline void next_cache_epoch(tfb_ctx* c) {
+    if (!c->cache_tag) return;
+    if (++c->gather_epoch < 2u) {   // wrapped: no tag of the previous cycle may match again
+        cudaMemsetAsync(c->cache_tag, 0, (size_t)c->total_entries * sizeof(unsigned long long), c->stream);
+        c->gather_epoch = 2u;
+    }
+    c->shard.cache_epoch = c->gather_epoch;
+}
 int launch_shard_push_frame(tfb_ctx* c, const uint16_t* depth_dev);
 int launch_model_maps(tfb_ctx* c);
 
