@@ -30,7 +30,7 @@ cudaError_t dmalloc(T** p, size_t n) { return cudaMalloc((void**)p, n * sizeof(T
 
 void free_all(tfb_ctx* c) {
     cudaFree(c->table); cudaFree(c->vba); cudaFree(c->vba_free); cudaFree(c->excess_free);
-    cudaFree(c->claim_key); cudaFree(c->claimed); cudaFree(c->bucket_bits); cudaFree(c->vis_type); cudaFree(c->vis_list[0]); cudaFree(c->vis_list[1]); cudaFree(c->own_list); cudaFree(c->cache_pool); cudaFree(c->cache_tag);
+    cudaFree(c->claim_key); cudaFree(c->claimed); cudaFree(c->bucket_bits); cudaFree(c->vis_type); cudaFree(c->vis_list[0]); cudaFree(c->vis_list[1]); cudaFree(c->cache_pool); cudaFree(c->cache_tag);
     cudaFree(c->minmax); cudaFree(c->raycast); cudaFree(c->dists_buf[0]); cudaFree(c->dists_buf[1]); cudaFree(c->depth_in); cudaFree(c->icp_partial);
     cudaFree(c->ds); cudaFree(c->l2_scratch); cudaFree(c->marks); cudaFree(c->shard_dev); cudaFree(c->sync_flags);
     for (int l = 0; l < MAX_LEVELS; ++l) {
@@ -245,13 +245,18 @@ int enqueue_tail(tfb_ctx* c) {
     TFB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_expect, 0));
     stamp(c, ST_RAYCAST);
     if (sharded(c)) {
-        // the collective frame (tfb_process_frame_sharded): every owner has integrated / every rank's rows have arrived
-        if ((r = launch_shard_barrier(c))) return r;
-        if ((r = launch_gather_foreign(c))) return r;
-        if ((r = launch_raycast_sharded(c, false))) return r;
-        if ((r = launch_shard_barrier(c))) return r;
-    } else if ((r = launch_raycast(c, true))) return r;
-    if ((r = launch_model_maps(c))) return r;
+        // The collective frame (tfb_process_frame_sharded).  Its two cross-GPU barriers — every owner has integrated; every
+        // rank's rows and marks have arrived — are not launches of their own: the gather publishes and waits in its
+        // prologue, the raycast's last CTA publishes and the model maps' CTAs wait.
+        auto next_epoch = [c]() { if (++c->sync_epoch == 0u) ++c->sync_epoch; return c->sync_epoch; };   // 0: "no barrier"
+        const unsigned int e1 = next_epoch(), e2 = next_epoch();
+        if ((r = launch_gather_foreign(c, e1))) return r;
+        if ((r = launch_raycast_sharded(c, false, e2))) return r;
+        if ((r = launch_model_maps(c, e2))) return r;
+    } else {
+        if ((r = launch_raycast(c, true))) return r;
+        if ((r = launch_model_maps(c))) return r;
+    }
     stamp(c, ST_PYR);
     return TFB_OK;
 }
@@ -294,6 +299,12 @@ int do_frame(tfb_ctx* c, const uint16_t* depth, size_t host_step_bytes, int* ok,
         if (c->timing) cudaEventRecord(c->ev_pre0, c->stream);
         const uint16_t* src = depth;
         cudaError_t e = cudaSuccess;
+        if (collective) {
+            // the sensor's rank pushes the frame into every rank's landing buffer; the others wait for its sequence number.
+            // Both happen here, beside the previous frame's tail, not in front of it.
+            r = c->push_src ? launch_shard_push_frame(c, c->push_src, true, c->frame_seq) : launch_wait_frame(c, c->frame_seq);
+            if (r) { c->stream = main_stream; return r; }
+        }
         if (host_step_bytes) {
             const size_t row = (size_t)c->p.cols * sizeof(uint16_t);
             e = cudaMemcpy2DAsync(c->depth_in, row, depth, host_step_bytes, row, c->p.rows, cudaMemcpyHostToDevice, c->stream);
@@ -441,7 +452,6 @@ int tfb_create(const tfb_params* p, void* stream, tfb_ctx** out) {
     ok(dmalloc(&c->vis_list[0], (size_t)c->total_entries));
     ok(dmalloc(&c->vis_list[1], (size_t)c->total_entries));
     if (p->shard_count > 1) {
-        ok(dmalloc(&c->own_list, (size_t)c->total_entries));
         // room for the foreign blocks ONE frame sees (256 MB at most), not for the scene: what does not fit is read from its owner
         const int cache_cap = p->num_blocks < (1 << 17) ? p->num_blocks : (1 << 17);
         ok(dmalloc(&c->cache_pool, (size_t)cache_cap * BLOCK3));
@@ -462,7 +472,7 @@ int tfb_create(const tfb_params* p, void* stream, tfb_ctx** out) {
     ok(cudaEventCreateWithFlags(&c->ev_expect, cudaEventDisableTiming));
     ok(cudaEventCreate(&c->ev_pre0));
     ok(cudaEventCreate(&c->ev_pre1));
-    ok(dmalloc(&c->depth_in, npx));
+    ok(dmalloc(&c->depth_in, 2 * npx));   // two landing buffers: the collective frame alternates (tfb_process_frame_sharded)
     {
         int w = p->cols, h = p->rows;
         for (int l = 0; l < MAX_LEVELS; ++l) {
@@ -486,7 +496,7 @@ int tfb_create(const tfb_params* p, void* stream, tfb_ctx** out) {
     ok(cudaMalloc((void**)&c->ds, sizeof(DevState) + 64 * sizeof(float)));
     ok(cudaMalloc((void**)&c->marks, (size_t)(2 + 2 * MARKS_CAP) * sizeof(unsigned int)));
     ok(cudaMalloc((void**)&c->shard_dev, sizeof(ShardView)));
-    ok(cudaMalloc((void**)&c->sync_flags, TFB_MAX_SHARDS * sizeof(unsigned int)));
+    ok(cudaMalloc((void**)&c->sync_flags, SHARD_FLAG_WORDS * sizeof(unsigned int)));
     ok(cudaMallocHost((void**)&c->hs, sizeof(DevState) + 64));   // + the sequence word k_icp_all publishes behind the block
     if (e == cudaSuccess) memset(c->hs, 0, sizeof(DevState) + 64);
     ok(cudaMallocHost((void**)&c->h_pose_stage, 64 * sizeof(float)));
@@ -516,7 +526,7 @@ int tfb_create(const tfb_params* p, void* stream, tfb_ctx** out) {
         free(tmp);
     }
     cudaMemsetAsync(c->marks, 0, 2 * sizeof(unsigned int), c->stream);
-    cudaMemsetAsync(c->sync_flags, 0, TFB_MAX_SHARDS * sizeof(unsigned int), c->stream);
+    cudaMemsetAsync(c->sync_flags, 0, SHARD_FLAG_WORDS * sizeof(unsigned int), c->stream);
     c->shard.rank = p->shard_rank; c->shard.count = p->shard_count; c->shard.marks_cap = MARKS_CAP;
     {
         tfb_shard_ptrs self;
@@ -818,10 +828,11 @@ int tfb_process_frame_sharded(tfb_ctx* c, const uint16_t* depth_dev_or_null, int
     if (c->p.shard_count > 1 && c->attached != (1u << c->p.shard_count) - 1u)
         return set_err(c, TFB_ERR_STATE, "attach every rank's buffers first (tfb_shard_attach)");
     if (c->p.shard_count <= 1) return depth_dev_or_null ? do_frame(c, depth_dev_or_null, 0, ok) : TFB_ERR_ARG;
-    int r;
-    if (depth_dev_or_null && (r = launch_shard_push_frame(c, depth_dev_or_null))) return r;
-    if ((r = launch_shard_barrier(c))) return r;   // the frame has arrived in every rank's frame buffer
-    r = do_frame(c, c->depth_in, 0, ok, true);
+    ++c->frame_seq;   // wraps: flags and acknowledgements are compared modulo 2^32
+    c->push_src = depth_dev_or_null;
+    const uint16_t* landing = c->depth_in + (size_t)(c->frame_seq & 1u) * c->p.cols * c->p.rows;
+    int r = do_frame(c, landing, 0, ok, true);
+    c->push_src = nullptr;
     if (r == TFB_OK && c->hs->shard_error) return set_err(c, TFB_ERR_STATE, "a cross-GPU barrier timed out: another rank stopped");
     return r;
 }
@@ -970,7 +981,7 @@ static const char* const KNAMES[K_COUNT] = {
     "k_icp_begin", "k_icp_iteration[L0]", "k_icp_iteration[L1]", "k_icp_iteration[L2]", "k_icp_iteration[L3]", "(unused)",
     "k_pose_set", "k_set_type3", "k_mark", "k_alloc", "k_visible_list", "k_list_flip", "k_integrate_begin", "k_integrate",
     "k_minmax_init", "k_expected_depths", "k_raycast", "k_icp_maps", "k_reset_scene", "k_icp_all", "k_render_grey",
-    "k_raycast_sharded", "k_model_maps", "k_pyramid_maps", "k_shard_barrier", "k_push_frame", "k_compact_owned", "k_gather_foreign"};
+    "k_raycast_sharded", "k_model_maps", "k_pyramid_maps", "k_shard_barrier", "k_push_frame", "k_wait_frame", "k_gather_foreign"};
 
 int tfb_ktiming_enable(tfb_ctx* c, int on) {
     if (!c) return TFB_ERR_ARG;

@@ -14,7 +14,7 @@ enum KernelId {
     K_BILATERAL = 0, K_DEPTH_PYR, K_POINTS_NORMALS, K_RESIZE_MAPS, K_COMPUTE_DISTS, K_TRUNCATE,
     K_ICP_BEGIN, K_ICP_L0, K_ICP_L1, K_ICP_L2, K_ICP_L3, K_POSE_UPDATE, K_POSE_SET,
     K_SET_TYPE3, K_MARK, K_ALLOC, K_VISIBLE_LIST, K_LIST_FLIP, K_INTEGRATE_BEGIN, K_INTEGRATE,
-    K_MINMAX_INIT, K_EXPECTED_DEPTHS, K_RAYCAST, K_ICP_MAPS, K_RESET_SCENE, K_ICP_ALL, K_RENDER_GREY, K_RAYCAST_SHARDED, K_MODEL_MAPS, K_PYR_MAPS, K_SHARD_BARRIER, K_PUSH_FRAME, K_COMPACT_OWNED, K_GATHER_FOREIGN, K_COUNT
+    K_MINMAX_INIT, K_EXPECTED_DEPTHS, K_RAYCAST, K_ICP_MAPS, K_RESET_SCENE, K_ICP_ALL, K_RENDER_GREY, K_RAYCAST_SHARDED, K_MODEL_MAPS, K_PYR_MAPS, K_SHARD_BARRIER, K_PUSH_FRAME, K_WAIT_FRAME, K_GATHER_FOREIGN, K_COUNT
 };
 constexpr int KT_MAX_EVENTS = 512;
 
@@ -73,9 +73,8 @@ struct DevState {
     unsigned int list_ticket;   // CTAs of k_visible_list that are done; the last one flips the lists
     int int_cursor;             // next visible-list position k_integrate hands out
     int shard_error;            // a cross-GPU barrier timed out
-    int n_own;                  // sharded scene: entries of the visible list whose payload this rank holds
     int n_cached;               // sharded scene: foreign visible blocks copied into the local cache this frame
-    int pad2_[1];
+    int pad2_[2];
 };
 
 // payload owner of a block when the scene is sharded (new; the reference is single-GPU).  A different mix than
@@ -99,8 +98,14 @@ struct ShardView {
     float4* raycast[TFB_MAX_SHARDS];
     unsigned int* marks[TFB_MAX_SHARDS];
     uint16_t* frame[TFB_MAX_SHARDS];
-    unsigned int* flags[TFB_MAX_SHARDS];
+    unsigned int* flags[TFB_MAX_SHARDS];   // SHARD_FLAG_WORDS words per rank, see below
 };
+// a rank's flag array: [0, TFB_MAX_SHARDS) the barrier epochs the other ranks have published here, then
+constexpr int SHARD_FLAG_FRAME = TFB_MAX_SHARDS;            // sequence number of the last frame rank 0 has pushed here
+constexpr int SHARD_FLAG_PUSH_TICKET = TFB_MAX_SHARDS + 1;  // local: CTAs of k_push_frame that are done
+constexpr int SHARD_FLAG_RAY_TICKET = TFB_MAX_SHARDS + 2;   // local: CTAs of k_raycast_sharded that are done
+constexpr int SHARD_FLAG_ACK = 2 * TFB_MAX_SHARDS;          // [ACK + r]: the last pushed frame rank r has finished reading
+constexpr int SHARD_FLAG_WORDS = 4 * TFB_MAX_SHARDS;
 
 struct LevelBuf {
     int w, h;
@@ -136,7 +141,6 @@ struct tfb_ctx {
     // render state
     int* vis_type;             // per slot (reference: uchar entriesVisibleType)
     int* vis_list[2];          // double-buffered visibleEntryIDs; DevState::cur_list says which is current
-    int* own_list;             // sharded scene only: the visible entries this rank integrates (compacted each frame)
     float2* minmax;            // (rows/8) x (cols/8)
     float4* raycast;           // rows x cols
     // frames
@@ -190,6 +194,8 @@ struct tfb_ctx {
     unsigned int* sync_flags;  // TFB_MAX_SHARDS words: the barrier epochs the other ranks have published here
     unsigned int sync_epoch;
     unsigned int gather_epoch;
+    unsigned int frame_seq;          // collective frames so far (tfb_process_frame_sharded)
+    const uint16_t* push_src;        // collective frame, rank with the sensor: the frame to push beside the previous frame's tail
     int frame_stage;           // 0 idle, 1 after tfb_frame_begin, 2 after tfb_frame_raycast
     bool frame_first;
     // software pipeline of the unsharded frame: preprocessing runs on stream_pre beside the deferred tail
@@ -270,9 +276,12 @@ int launch_expected_depths(tfb_ctx* c, bool reset_image = false);
 int launch_icp_maps(tfb_ctx* c, float4* points, float4* normals, bool do_raycast = true);
 int launch_render_grey(tfb_ctx* c, uchar4* out);
 int launch_raycast(tfb_ctx* c, bool update_visible);
-int launch_raycast_sharded(tfb_ctx* c, bool viewer);
+// publish_epoch != 0: the last CTA to finish publishes that barrier epoch to every rank (this rank's rows and marks are out)
+int launch_raycast_sharded(tfb_ctx* c, bool viewer, unsigned int publish_epoch = 0u);
 int launch_shard_barrier(tfb_ctx* c);
-int launch_gather_foreign(tfb_ctx* c);
+// barrier_epoch != 0: the launch is also the cross-GPU barrier in front of it (publishes, then every CTA waits)
+int launch_gather_foreign(tfb_ctx* c, unsigned int barrier_epoch = 0u);
+int launch_wait_frame(tfb_ctx* c, unsigned int seq);
 // Sharded scene: a new generation of the foreign-block cache (after anything that changes voxels, and for every gather).
 // 0 is the generation of the zeroed tags and 1 the one the device-resident ShardView carries: neither is ever handed out.
 inline void next_cache_epoch(tfb_ctx* c) {
@@ -283,7 +292,9 @@ inline void next_cache_epoch(tfb_ctx* c) {
     }
     c->shard.cache_epoch = c->gather_epoch;
 }
-int launch_shard_push_frame(tfb_ctx* c, const uint16_t* depth_dev);
-int launch_model_maps(tfb_ctx* c);
+// collective: into landing buffer (seq & 1) of every rank, and the last CTA publishes seq in every rank's frame flag
+int launch_shard_push_frame(tfb_ctx* c, const uint16_t* depth_dev, bool collective = false, unsigned int seq = 0u);
+// wait_epoch != 0: every CTA first waits until all ranks have published that epoch (their raycast rows have arrived)
+int launch_model_maps(tfb_ctx* c, unsigned int wait_epoch = 0u);
 
 }  // namespace tfb
