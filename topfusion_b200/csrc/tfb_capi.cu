@@ -288,10 +288,17 @@ int do_frame(tfb_ctx* c, const uint16_t* depth, size_t host_step_bytes, int* ok,
     TFB_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));
     TFB_CUDA(c, cudaStreamWaitEvent(c->stream_pre, c->ev_fork, 0));
     const bool had_tail = c->tail_pending;
-    if (had_tail) { if ((r = enqueue_tail(c))) return r; }
-    else { stamp(c, ST_ALLOC); stamp(c, ST_INTEG); stamp(c, ST_EXPECT); stamp(c, ST_RAYCAST); stamp(c, ST_PYR); }
-    // this frame's metres image must not overwrite the one the tail above is still reading
+    // this frame's metres image must not overwrite the one the tail is still reading
     float* dists = (c->tail_dists == c->dists_buf[0]) ? c->dists_buf[1] : c->dists_buf[0];
+    auto tail = [&]() -> int {
+        if (had_tail) return enqueue_tail(c);
+        stamp(c, ST_ALLOC); stamp(c, ST_INTEG); stamp(c, ST_EXPECT); stamp(c, ST_RAYCAST); stamp(c, ST_PYR);
+        return TFB_OK;
+    };
+    // One GPU: the tail is enqueued first, so that its expected-depth image — which also runs on the second stream, and
+    // which the raycast waits for — is not queued behind the preprocessing.  Sharded: the raycast starts later (behind the
+    // integration barrier and the gather), and the preprocessing should be out of its way by then, so it goes first.
+    if (!collective && (r = tail())) return r;
     c->dists = dists;
     {
         cudaStream_t main_stream = c->stream;
@@ -316,6 +323,7 @@ int do_frame(tfb_ctx* c, const uint16_t* depth, size_t host_step_bytes, int* ok,
         c->stream = main_stream;
         if (r) return r;
     }
+    if (collective && (r = tail())) return r;
     TFB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
     stamp(c, ST_ICP);
     if (first) {
