@@ -30,7 +30,7 @@ cudaError_t dmalloc(T** p, size_t n) { return cudaMalloc((void**)p, n * sizeof(T
 
 void free_all(tfb_ctx* c) {
     cudaFree(c->table); cudaFree(c->vba); cudaFree(c->vba_free); cudaFree(c->excess_free);
-    cudaFree(c->claim_key); cudaFree(c->claimed); cudaFree(c->bucket_bits); cudaFree(c->vis_type); cudaFree(c->vis_list[0]); cudaFree(c->vis_list[1]); cudaFree(c->cache_tag);
+    cudaFree(c->claim_key); cudaFree(c->claimed); cudaFree(c->bucket_bits); cudaFree(c->vis_type); cudaFree(c->vis_list[0]); cudaFree(c->vis_list[1]); cudaFree(c->cache_pool); cudaFree(c->cache_tag);
     cudaFree(c->minmax); cudaFree(c->raycast); cudaFree(c->dists_buf[0]); cudaFree(c->dists_buf[1]); cudaFree(c->depth_in); cudaFree(c->icp_partial);
     cudaFree(c->ds); cudaFree(c->l2_scratch); cudaFree(c->marks); cudaFree(c->shard_dev); cudaFree(c->sync_flags);
     for (int l = 0; l < MAX_LEVELS; ++l) {
@@ -395,13 +395,6 @@ int do_frame(tfb_ctx* c, const uint16_t* depth, size_t host_step_bytes, int* ok,
     return TFB_OK;
 }
 
-// sharded scene: room behind the voxel pool for the foreign blocks ONE frame sees (256 MB at most), not for the scene:
-// what does not fit is read from its owner
-inline int sharded_cache_blocks(const tfb_params* p) {
-    if (p->shard_count <= 1) return 0;
-    return p->num_blocks < (1 << 17) ? p->num_blocks : (1 << 17);
-}
-
 }  // namespace
 
 #define TFB_SETTLE(c)                       \
@@ -438,7 +431,6 @@ int tfb_create(const tfb_params* p, void* stream, tfb_ctx** out) {
     if (p->num_buckets <= 0 || (p->num_buckets & (p->num_buckets - 1))) return TFB_ERR_ARG;
     if (p->num_blocks <= 0 || p->excess_size <= 0 || p->voxel_size <= 0 || p->mu <= 0) return TFB_ERR_ARG;
     if (p->shard_count < 1 || p->shard_count > TFB_MAX_SHARDS || p->shard_rank < 0 || p->shard_rank >= p->shard_count) return TFB_ERR_ARG;
-    if ((long long)p->num_blocks + sharded_cache_blocks(p) > 0x7fffffffLL / BLOCK3) return TFB_ERR_ARG;   // voxel indices are 31 bits
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return TFB_ERR_CUDA;  // no CPU fallback, by design
 
@@ -458,7 +450,7 @@ int tfb_create(const tfb_params* p, void* stream, tfb_ctx** out) {
 
     const size_t npx = (size_t)p->cols * p->rows;
     ok(dmalloc(&c->table, (size_t)c->total_entries));
-    ok(dmalloc(&c->vba, ((size_t)p->num_blocks + sharded_cache_blocks(p)) * BLOCK3));
+    ok(dmalloc(&c->vba, (size_t)p->num_blocks * BLOCK3));
     ok(dmalloc(&c->vba_free, (size_t)p->num_blocks));
     ok(dmalloc(&c->excess_free, (size_t)p->excess_size));
     ok(dmalloc(&c->claim_key, (size_t)c->total_entries));
@@ -469,12 +461,11 @@ int tfb_create(const tfb_params* p, void* stream, tfb_ctx** out) {
     ok(dmalloc(&c->vis_list[1], (size_t)c->total_entries));
     if (p->shard_count > 1) {
         // room for the foreign blocks ONE frame sees (256 MB at most), not for the scene: what does not fit is read from its owner
-        const int cache_cap = sharded_cache_blocks(p);
+        const int cache_cap = p->num_blocks < (1 << 17) ? p->num_blocks : (1 << 17);
+        ok(dmalloc(&c->cache_pool, (size_t)cache_cap * BLOCK3));
         ok(dmalloc(&c->cache_tag, (size_t)c->total_entries));
         if (e == cudaSuccess) cudaMemsetAsync(c->cache_tag, 0, (size_t)c->total_entries * sizeof(unsigned long long), c->stream);
-        c->cache_pool = reinterpret_cast<unsigned int*>(c->vba) + (size_t)p->num_blocks * BLOCK3;
         c->shard.cache_pool = c->cache_pool; c->shard.cache_tag = c->cache_tag; c->shard.cache_cap = cache_cap;
-        c->shard.cache_base = p->num_blocks * BLOCK3;
         c->shard.cache_epoch = c->gather_epoch = 1u;   // the zeroed tags carry epoch 0: no copy yet
     }
     ok(dmalloc(&c->minmax, npx / (MINMAX_SUB * MINMAX_SUB)));

@@ -89,12 +89,10 @@ __host__ __device__ __forceinline__ int owner_rank(int bx, int by, int bz, int c
 // what a rank needs of every rank (itself included) to cast rays through a sharded scene: kernel parameter, by value
 struct ShardView {
     int rank, count, marks_cap, cache_cap;
-    // local copies of the foreign visible blocks of this frame (k_gather_foreign) live in the tail of the local voxel pool,
-    // from voxel index cache_base on, so that a ray addresses owned and copied blocks alike; tag[slot] = epoch << 32 | copy
+    // local copies of the foreign visible blocks of this frame (k_gather_foreign): tag[slot] = epoch << 32 | cache index
     const unsigned int* cache_pool;
     const unsigned long long* cache_tag;
-    unsigned int cache_epoch;
-    int cache_base;
+    unsigned int cache_epoch, pad_;
     const int4* table[TFB_MAX_SHARDS];
     const unsigned int* vba[TFB_MAX_SHARDS];
     float4* raycast[TFB_MAX_SHARDS];
@@ -191,7 +189,7 @@ struct tfb_ctx {
     tfb::ShardView* shard_dev; // device copy (kernels that take it by pointer)
     unsigned int attached;     // bit r set once rank r's buffers are attached
     unsigned int* marks;       // incoming visibility marks: [0] count, [1] pad, then 2 words per mark
-    unsigned int* cache_pool;        // sharded scene: this frame's copies of the foreign visible blocks (2 KB each): the tail of vba
+    unsigned int* cache_pool;        // sharded scene: this frame's copies of the foreign visible blocks (2 KB each)
     unsigned long long* cache_tag;   // per hash slot: epoch << 32 | index into cache_pool
     unsigned int* sync_flags;  // TFB_MAX_SHARDS words: the barrier epochs the other ranks have published here
     unsigned int sync_epoch;
