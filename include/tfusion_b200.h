@@ -188,8 +188,11 @@ typedef struct tfb_shard_ptrs {
     void* vba;       /* num_blocks x 2 KB voxel pool */
     void* raycast;   /* rows x cols float4 raycast result */
     void* marks;     /* incoming visibility marks: u32 count, pad, then 2 x u32 per mark */
-    void* frame;     /* rows x cols u16: the depth frame rank 0 pushes to every rank (tfb_shard_push_frame) */
-    void* flags;     /* TFB_MAX_SHARDS x u32: flags[r] = last barrier epoch rank r has reached (tfb_shard_barrier) */
+    void* frame;     /* 2 x rows x cols u16: landing buffers for the depth frame the sensor's rank pushes to every rank
+                      * (tfb_shard_push_frame uses the first; tfb_process_frame_sharded alternates) */
+    void* flags;     /* 4 x TFB_MAX_SHARDS x u32, written by the peers: [r] = last barrier epoch rank r has reached,
+                      * [TFB_MAX_SHARDS] = sequence number of the last frame pushed here, [2*TFB_MAX_SHARDS + r] = last pushed
+                      * frame rank r has finished reading; the words in between are this rank's own tickets */
 } tfb_shard_ptrs;
 TFB_API int tfb_shard_local_ptrs(tfb_ctx* c, tfb_shard_ptrs* out);
 TFB_API int tfb_shard_attach(tfb_ctx* c, int rank, const tfb_shard_ptrs* peer);
@@ -204,9 +207,13 @@ TFB_API int tfb_ipc_close(void* dev_ptr);
  *                       single-process emulation orders the stages by stream order instead).  A rank that waits longer
  *                       than ~10 s gives up; the frame then reports TFB_ERR_STATE.
  * tfb_frame_begin(c, NULL) then tracks the frame in the context's frame buffer. */
-/* tfb_process_frame_sharded: the whole sharded frame in ONE call per rank — push (the rank that passes a frame, normally
- * rank 0; the others pass NULL), barrier, then the software-pipelined frame of tfb_process_frame with the two remaining
- * barriers inside the deferred tail.  *ok is operator()'s verdict, identical on every rank.  Collective: every rank calls it
+/* tfb_process_frame_sharded: the whole sharded frame in ONE call per rank, software-pipelined like tfb_process_frame.  The
+ * rank that passes a frame (the sensor's; always the same one, normally rank 0 — the others pass NULL) pushes it into a
+ * landing buffer of every rank on the second stream, beside the previous frame's tail; the receivers wait for its sequence
+ * number there and acknowledge when they have read it.  The tail's two cross-GPU barriers are folded into its kernels
+ * (k_gather_foreign publishes "integrated" and waits; k_raycast_sharded's last CTA publishes "rows out", k_model_maps
+ * waits), so the sharded frame has no barrier launch.  *ok is operator()'s verdict, identical on every rank.  Real
+ * multi-GPU only (kernels of different ranks wait on one another).  Collective: every rank calls it
  * for every frame, in the same order; with defer_tail, so is every call that finishes a pending tail on a sharded context
  * (tfb_sync, tfb_get_counters, the tfb_export_* family, tfb_render_image ...). */
 TFB_API int tfb_process_frame_sharded(tfb_ctx* c, const uint16_t* depth_dev_or_null, int* ok);
