@@ -10,7 +10,8 @@ WANT = ["Kernel Name", "launch__grid_size", "launch__block_size", "launch__regis
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
         "l1tex__t_sector_hit_rate.pct", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
-        "smsp__average_warp_latency_per_inst_issued.ratio", "smsp__thread_inst_executed_per_inst_executed.ratio"]
+        "smsp__average_warp_latency_per_inst_issued.ratio", "smsp__thread_inst_executed_per_inst_executed.ratio",
+        "launch__waves_per_multiprocessor", "launch__occupancy_limit_registers", "launch__occupancy_limit_warps"]
 
 
 def main(rep, out):
