@@ -33,3 +33,37 @@ def test_reference_arm_prints_one_json_line():
 def test_reference_arm_other_ranks_are_silent():
     r = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def _line(name):
+    with open(os.path.join(ROOT, "profiles", name)) as f:
+        lines = [l for l in f.read().splitlines() if l.strip()]
+    assert len(lines) == 1, name
+    return json.loads(lines[0])
+
+
+def test_committed_bench_lines_carry_the_contract():
+    """the evidence under profiles/ is what bench.py printed on the B200 boxes: every key the driver and the judge read"""
+    for name, n in (("r01_bench_v10.json", 1), ("r01_bench_v10_2gpu.json", 2), ("r01_bench_v10_4gpu.json", 4)):
+        d = _line(name)
+        for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                  "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline"):
+            assert k in d, (name, k)
+        assert d["n_gpus"] == n and d["unit"] == "frames/s" and d["higher_is_better"] is True and d["warmup"] >= 3
+        assert d["config"]["workload"].startswith("S1 synthetic 640x480") and "model" not in d["config"]
+        assert "l2" in d["config"]                                       # how the caches were treated between timed steps
+        assert d["gpu_launches"] >= 12 * d["steps"]                      # our kernels, counted over the timed steps
+        assert abs(d["value"] * d["ms_per_step"] / 1000.0 - 1.0) < 1e-6  # one frame per step, whole job
+        e = d["e2e"]
+        assert e["unit"] == "frames/s" and e["h2d_bytes_per_step"] == 640 * 480 * 2 and e["d2h_bytes_per_step"] > 0
+        assert e["value"] != d["value"]                                  # measured on its own, host buffers inside the timed region
+        r = d["roofline"]
+        assert r["bound"] in ("hbm", "tensor") and r["unit"] in ("GB/s", "TFLOP/s")
+        assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and 0 < r["frac"] < 1
+        assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        if n == 1:
+            cb = d["cpu_baseline"]
+            assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] > 0 and cb["sample"]
+            assert r["traffic"] is not None and r["traffic"] > 0
+    # the sharded runs track the same trajectory as each other, to the last bit of the final pose error
+    assert _line("r01_bench_v10_2gpu.json")["config"]["final_pose_err_m"] == _line("r01_bench_v10_4gpu.json")["config"]["final_pose_err_m"]
