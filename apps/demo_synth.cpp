@@ -3,7 +3,10 @@
 // renderImage + download, getCameraPose) without highgui / viz / OpenNI.  Frames are 16-bit PGMs named %04d.pgm
 // (what demo.cpp reads), e.g. written by `python -m topfusion_b200.synth_cli`.
 //
-//   demo_synth <frame_dir> [n_frames] [--corrected] [--out view.pgm]
+//   demo_synth <frame_dir> [n_frames] [--corrected] [--out view.pgm] [--ring]
+// --ring: the input side as a decode-ahead ring of page-locked frames (io::FrameRing) handed to operator() in host memory,
+// instead of demo.cpp's synchronous imread + upload per frame; same poses, same view.
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -67,6 +70,29 @@ struct TopFuApp {
         return true;
     }
 
+    // the same loop with the frames decoded ahead into page-locked memory and uploaded asynchronously inside operator()
+    bool execute_ring(const std::string& dir, int n_frames) {
+        TopFu& topfu = *topfu_;
+        io::FrameRing ring(dir, 4, 0, n_frames);
+        const auto t0 = std::chrono::steady_clock::now();
+        int i = 0;
+        while (const io::HostFrame* f = ring.next()) {
+            const bool has_image = topfu(*f);
+            const int index = f->index;
+            ring.release(f);   // the slot may be refilled from here on
+            if (has_image) show_raycasted(topfu);
+            Affine3f pose = topfu.getCameraPose();
+            std::printf("frame %3d ok=%d t=(% .5f % .5f % .5f) voxel-updates=%lld\n", index, (int)has_image, pose.matrix(0, 3),
+                        pose.matrix(1, 3), pose.matrix(2, 3), topfu.voxelUpdatesLastFrame());
+            ++i;
+        }
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (!ring.error().empty()) return std::cout << "Can't grab: " << ring.error() << std::endl, false;
+        std::printf("ring: %d frames in %.1f ms (decode + upload + operator() + render), consumer waited %.1f ms for the decoder, %s memory\n",
+                    i, ms, ring.consumerWaitMs(), ring.pinned() ? "page-locked" : "pageable");
+        return i == n_frames;
+    }
+
     // what demo.cpp's take_cloud stub (apps/demo.cpp:70-77) is there for: the reconstruction as a point cloud
     void take_cloud() {
         cuda::DeviceArray<float> cloud;
@@ -91,13 +117,14 @@ struct TopFuApp {
 };
 
 int main(int argc, char* argv[]) {
-    if (argc < 2) return std::cout << "usage: demo_synth <frame_dir> [n_frames] [--corrected] [--out view.pgm]" << std::endl, 2;
+    if (argc < 2) return std::cout << "usage: demo_synth <frame_dir> [n_frames] [--corrected] [--out view.pgm] [--ring]" << std::endl, 2;
     int n = 20;
-    bool corrected = false;
+    bool corrected = false, use_ring = false;
     std::string out;
     for (int i = 2; i < argc; ++i) {
         if (!std::strcmp(argv[i], "--corrected")) corrected = true;
         else if (!std::strcmp(argv[i], "--out") && i + 1 < argc) out = argv[++i];
+        else if (!std::strcmp(argv[i], "--ring")) use_ring = true;
         else n = std::atoi(argv[i]);
     }
     int device = 0;
@@ -108,7 +135,7 @@ int main(int argc, char* argv[]) {
     OpenNISource capture;  // kept for call-sequence parity with demo.cpp; frames come from files
     (void)capture;
     TopFuApp app(corrected);
-    bool ok = app.execute(argv[1], n);
+    bool ok = use_ring ? app.execute_ring(argv[1], n) : app.execute(argv[1], n);
     if (!out.empty()) app.save_view(out);
     if (ok) app.take_cloud();
     return ok ? 0 : 1;

@@ -8,6 +8,7 @@
 #include <tfusion/SceneParams.hpp>
 #include <tfusion/cuda/projective_icp.hpp>
 #include <tfusion/cuda/imgproc.hpp>
+#include <io/frame_ring.hpp>
 
 struct tfb_ctx;
 
@@ -84,6 +85,10 @@ public:
     void reset();
 
     bool operator()(const cuda::Depth& dpeth, const cuda::Image& image = cuda::Image());
+    // addition: the frame still in (preferably page-locked) host memory, e.g. a slot of io::FrameRing.  The upload is an
+    // asynchronous copy on the library's second stream, beside the previous frame's integration and raycast, instead of
+    // the synchronous Depth::upload in front of the call; the buffer may be reused as soon as the call returns.
+    bool operator()(const io::HostFrame& depth);
 
     void renderImage(cuda::image4u& image);
 
@@ -108,6 +113,7 @@ private:
     cv::Ptr<cuda::ProjectiveICP> icp_;
     tfb_ctx* ctx_;
     cuda::Depth dense_depth_;  // staging when the caller's frame is pitched
+    bool finish_frame(int ok);
 };
 
 }  // namespace tfusion

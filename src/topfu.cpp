@@ -133,6 +133,20 @@ bool TopFu::operator()(const cuda::Depth& depth, const cuda::Image&) {
     }
     int ok = 0;
     TF_CHECK(tfb_process_frame_device(ctx_, src, &ok));
+    return finish_frame(ok);
+}
+
+bool TopFu::operator()(const io::HostFrame& depth) {
+    if (!depth.data || depth.rows != params_.rows || depth.cols != params_.cols)
+        cuda::error("depth frame size differs from TopFuParams", __FILE__, __LINE__, "TopFu::operator()");
+    TF_CHECK(tfb_set_icp_params(ctx_, icp_->getDistThreshold(), icp_->getAngleThreshold(), &icp_->iterations()[0]));
+    int ok = 0;
+    TF_CHECK(tfb_process_frame(ctx_, depth.data, depth.step, &ok));
+    return finish_frame(ok);
+}
+
+// what operator() does once the library has the verdict (topfu.cpp:252, 263-264)
+bool TopFu::finish_frame(int ok) {
     if (scene_config_.print_pose && ok) {
         Affine3f p = getCameraPose();
         std::cout << "pose:" << std::endl;
