@@ -30,7 +30,10 @@ def test_public_symbols_of_the_reference_api_are_exported():
                 "tfusion::cuda::DeviceMemory2D::upload(", "tfusion::cuda::DeviceMemory2D::download(",
                 "tfusion::cuda::ProjectiveICP::setIterationsNum(", "tfusion::cuda::ProjectiveICP::estimateTransform(",
                 "tfusion::cuda::depthBilateralFilter(", "tfusion::cuda::computePointNormals(", "tfusion::cuda::resizePointsNormals(",
-                "tfusion::SampledScopeTime::SampledScopeTime(double&)", "tfusion::OpenNISource::open(int)"):
+                "tfusion::SampledScopeTime::SampledScopeTime(double&)", "tfusion::OpenNISource::open(int)",
+                # additions in front of / behind the path
+                "tfusion::TopFu::operator()(tfusion::io::HostFrame const&)", "tfusion::io::FrameRing::next()",
+                "tfusion::io::readPgm16(", "tfusion::TopFu::extractPoints(", "tfusion::TopFu::saveScene("):
         assert sym in out, sym
 
 
