@@ -34,6 +34,15 @@ bool header_int(FILE* f, int& value) {
 
 struct Header { bool plain; int cols, rows, maxval; };
 
+// big-endian file samples -> host order (a no-op on a big-endian host)
+inline void swap_rows(unsigned short* row, int n) {
+#if defined(__BYTE_ORDER__) && __BYTE_ORDER__ == __ORDER_BIG_ENDIAN__
+    (void)row; (void)n;
+#else
+    for (int x = 0; x < n; ++x) row[x] = __builtin_bswap16(row[x]);
+#endif
+}
+
 bool read_header(FILE* f, Header& h) {
     const int p = std::fgetc(f), k = std::fgetc(f);
     if (p != 'P' || (k != '5' && k != '2')) return false;
@@ -72,11 +81,19 @@ bool readPgm16(const std::string& path, unsigned short* dst, size_t dst_step, in
             }
         }
     } else if (ok) {
-        std::vector<unsigned char> raw((size_t)cols * 2);
-        for (int y = 0; y < rows; ++y) {
-            if (std::fread(raw.data(), 1, raw.size(), f) != raw.size()) { ok = false; break; }
+        // the raster goes straight into the destination (one read when the rows are dense), then the big-endian samples are
+        // swapped in place — a loop the compiler turns into byte shuffles; at 4 000 frames/s the decode must not cost more
+        // than the frame
+        const size_t row_bytes = (size_t)cols * 2;
+        if (dst_step == row_bytes) {
+            ok = std::fread(dst, 1, row_bytes * rows, f) == row_bytes * rows;
+        } else {
+            for (int y = 0; ok && y < rows; ++y)
+                ok = std::fread(reinterpret_cast<char*>(dst) + (size_t)y * dst_step, 1, row_bytes, f) == row_bytes;
+        }
+        for (int y = 0; ok && y < rows; ++y) {
             unsigned short* row = reinterpret_cast<unsigned short*>(reinterpret_cast<char*>(dst) + (size_t)y * dst_step);
-            for (int x = 0; x < cols; ++x) row[x] = (unsigned short)((raw[2 * x] << 8) | raw[2 * x + 1]);   // big-endian samples
+            swap_rows(row, cols);
         }
     }
     std::fclose(f);
@@ -89,13 +106,15 @@ std::string FrameRing::path(int index) const {
     return dir_ + name;
 }
 
-FrameRing::FrameRing(const std::string& dir, int slots, int first, int count, bool allow_pageable)
-    : dir_(dir), first_(first), count_(count), cols_(0), rows_(0), pinned_(true), stop_(false), done_(false), produce_at_(0),
-      consume_at_(0), wait_ms_(0.0) {
+FrameRing::FrameRing(const std::string& dir, int slots, int first, int count, bool allow_pageable, int decoders)
+    : dir_(dir), first_(first), count_(count), cols_(0), rows_(0), pinned_(true), stop_(false), claim_at_(0),
+      end_at_(count >= 0 ? count : 0x7fffffff), consume_at_(0), wait_ms_(0.0) {
     if (slots < 2) slots = 2;
+    if (decoders < 1) decoders = 1;
+    if (decoders > slots) decoders = slots;
     if (count_ == 0 || !probePgm16(path(first_), cols_, rows_)) {
         if (count_ != 0) error_ = "cannot read " + path(first_);
-        done_ = true;
+        end_at_ = 0;
         return;
     }
     const size_t bytes = (size_t)cols_ * rows_ * sizeof(unsigned short);
@@ -109,6 +128,7 @@ FrameRing::FrameRing(const std::string& dir, int slots, int first, int count, bo
             for (Slot& s : slots_) {   // all slots of one kind
                 tfb_host_free_pinned(s.mem);
                 s.mem = static_cast<unsigned short*>(std::malloc(bytes));
+                if (!s.mem) throw std::runtime_error("FrameRing: out of host memory");
             }
             pinned_ = false;
         }
@@ -121,7 +141,7 @@ FrameRing::FrameRing(const std::string& dir, int slots, int first, int count, bo
         slots_.push_back(s);
     }
     for (Slot& s : slots_) s.frame.data = s.mem;
-    producer_ = std::thread(&FrameRing::produce, this);
+    for (int i = 0; i < decoders; ++i) decoders_.emplace_back(&FrameRing::produce, this);
 }
 
 FrameRing::~FrameRing() {
@@ -130,41 +150,47 @@ FrameRing::~FrameRing() {
         stop_ = true;
     }
     cv_.notify_all();
-    if (producer_.joinable()) producer_.join();
+    for (std::thread& t : decoders_)
+        if (t.joinable()) t.join();
     for (Slot& s : slots_) {
         if (pinned_) tfb_host_free_pinned(s.mem);
         else std::free(s.mem);
     }
 }
 
+// A decoder thread: claim the next position of the sequence once its slot is free, decode, mark the slot ready.  Positions
+// are claimed in order and a slot serves positions p, p + slots, ...: the consumer frees them in order, so with several
+// decoders the files are still delivered in sequence.  The first position that cannot be read ends the sequence there
+// (end_at_), whatever later positions other decoders have already finished.
 void FrameRing::produce() {
     const int n = (int)slots_.size();
-    for (int pos = 0;; ++pos) {
-        Slot& s = slots_[pos % n];
+    for (;;) {
+        int pos;
         {
             std::unique_lock<std::mutex> g(m_);
-            cv_.wait(g, [&] { return stop_ || s.state == FREE; });
-            if (stop_) return;
-            if (count_ >= 0 && pos >= count_) { done_ = true; cv_.notify_all(); return; }
-            s.state = FILLING;
+            cv_.wait(g, [&] { return stop_ || claim_at_ >= end_at_ || slots_[claim_at_ % n].state == FREE; });
+            if (stop_ || claim_at_ >= end_at_) return;
+            pos = claim_at_++;
+            slots_[pos % n].state = FILLING;
         }
-        const int index = first_ + pos;
-        const std::string file = path(index);
+        Slot& s = slots_[pos % n];
+        const std::string file = path(first_ + pos);
         const bool ok = readPgm16(file, s.mem, s.frame.step, cols_, rows_);
         std::lock_guard<std::mutex> g(m_);
         if (!ok) {
-            // an open-ended sequence ends at the first file that is not there; anything else is an error
-            FILE* f = std::fopen(file.c_str(), "rb");
-            if (f) std::fclose(f);
-            if (f || count_ >= 0) error_ = "cannot read " + file;
+            if (pos < end_at_) {
+                end_at_ = pos;
+                // an open-ended sequence ends at the first file that is not there; anything else is an error
+                FILE* f = std::fopen(file.c_str(), "rb");
+                if (f) std::fclose(f);
+                error_ = (f || count_ >= 0) ? "cannot read " + file : std::string();
+            }
             s.state = FREE;
-            done_ = true;
             cv_.notify_all();
             return;
         }
-        s.frame.index = index;
+        s.frame.index = first_ + pos;
         s.state = READY;
-        produce_at_ = pos + 1;
         cv_.notify_all();
     }
 }
@@ -173,12 +199,13 @@ const HostFrame* FrameRing::next() {
     if (slots_.empty()) return nullptr;
     Slot& s = slots_[consume_at_ % (int)slots_.size()];
     std::unique_lock<std::mutex> g(m_);
-    if (s.state != READY && !(done_ && produce_at_ == consume_at_)) {
+    auto settled = [&] { return consume_at_ >= end_at_ || (s.state == READY && s.frame.index == first_ + consume_at_); };
+    if (!settled()) {
         const auto t0 = std::chrono::steady_clock::now();
-        cv_.wait(g, [&] { return s.state == READY || (done_ && produce_at_ == consume_at_); });
+        cv_.wait(g, settled);
         wait_ms_ += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     }
-    if (s.state != READY) return nullptr;
+    if (consume_at_ >= end_at_) return nullptr;
     s.state = HELD;
     ++consume_at_;
     return &s.frame;
@@ -215,11 +242,11 @@ int tfio_probe_pgm16(const char* path, int* cols, int* rows) {
 int tfio_read_pgm16(const char* path, unsigned short* dst, size_t dst_step, int cols, int rows) {
     return (path && tfusion::io::readPgm16(path, dst, dst_step, cols, rows)) ? 1 : 0;
 }
-void* tfio_ring_open(const char* dir, int slots, int first, int count, int allow_pageable) {
+void* tfio_ring_open(const char* dir, int slots, int first, int count, int allow_pageable, int decoders) {
     if (!dir) return nullptr;
     try {
         RingHandle* h = new RingHandle();
-        h->ring = new FrameRing(dir, slots, first, count, allow_pageable != 0);
+        h->ring = new FrameRing(dir, slots, first, count, allow_pageable != 0, decoders);
         return h;
     } catch (const std::exception&) {
         return nullptr;

@@ -21,7 +21,7 @@ def io():
     L.tfio_probe_pgm16.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.tfio_read_pgm16.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int]
     L.tfio_ring_open.restype = C.c_void_p
-    L.tfio_ring_open.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.tfio_ring_open.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     L.tfio_ring_next.argtypes = [C.c_void_p, C.POINTER(C.POINTER(C.c_uint16)), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                  C.POINTER(C.c_size_t), C.POINTER(C.c_int)]
     L.tfio_ring_release.argtypes = [C.c_void_p, C.c_int]
@@ -121,13 +121,14 @@ def drain(io, ring, hold=1, pause=0.0):
     return out
 
 
-@pytest.mark.parametrize("slots,hold,pause,count", [(2, 1, 0.0, -1), (3, 2, 0.0, -1), (4, 1, 0.003, -1), (3, 1, 0.0, 7)])
-def test_ring_delivers_the_sequence_in_order(io, tmp_path, slots, hold, pause, count):
+@pytest.mark.parametrize("slots,hold,pause,count,decoders", [(2, 1, 0.0, -1, 1), (3, 2, 0.0, -1, 2), (4, 1, 0.003, -1, 3),
+                                                             (3, 1, 0.0, 7, 2), (6, 3, 0.0, -1, 6), (4, 1, 0.0, 11, 4)])
+def test_ring_delivers_the_sequence_in_order(io, tmp_path, slots, hold, pause, count, decoders):
     rng = np.random.default_rng(slots * 10 + hold)
     frames = [rng.integers(0, 65536, (24, 32)).astype(np.uint16) for _ in range(11)]
     for i, f in enumerate(frames):
         write_pgm(str(tmp_path / ("%04d.pgm" % (i + 2))), f)      # the sequence starts at 0002.pgm
-    ring = io.tfio_ring_open(str(tmp_path).encode(), slots, 2, count, 1)
+    ring = io.tfio_ring_open(str(tmp_path).encode(), slots, 2, count, 1, decoders)
     assert ring
     try:
         got = drain(io, ring, hold=hold, pause=pause)
@@ -145,27 +146,27 @@ def test_ring_reports_a_broken_file_and_can_be_closed_early(io, tmp_path):
         write_pgm(str(tmp_path / ("%04d.pgm" % i)), a + i)
     with open(str(tmp_path / "0003.pgm"), "r+b") as f:
         f.truncate(100)
-    ring = io.tfio_ring_open(str(tmp_path).encode(), 3, 0, -1, 1)
+    ring = io.tfio_ring_open(str(tmp_path).encode(), 3, 0, -1, 1, 2)
     try:
         got = drain(io, ring)
         assert [i for i, _ in got] == [0, 1, 2] and b"0003.pgm" in io.tfio_ring_error(ring)
     finally:
         io.tfio_ring_close(ring)
     # a fixed-length sequence that runs out of files is an error too
-    ring = io.tfio_ring_open(str(tmp_path).encode(), 3, 4, 5, 1)
+    ring = io.tfio_ring_open(str(tmp_path).encode(), 3, 4, 5, 1, 3)
     try:
         assert [i for i, _ in drain(io, ring)] == [4, 5] and b"0006.pgm" in io.tfio_ring_error(ring)
     finally:
         io.tfio_ring_close(ring)
     # closing while the producer is ahead and a frame is still held must not hang
-    ring = io.tfio_ring_open(str(tmp_path).encode(), 2, 0, 3, 1)
+    ring = io.tfio_ring_open(str(tmp_path).encode(), 2, 0, 3, 1, 2)
     data, rows, cols, step, index = C.POINTER(C.c_uint16)(), C.c_int(), C.c_int(), C.c_size_t(), C.c_int()
     assert io.tfio_ring_next(ring, C.byref(data), C.byref(rows), C.byref(cols), C.byref(step), C.byref(index)) == 1
     io.tfio_ring_close(ring)
     # an empty directory: no frames, an error naming the first file
     empty = tmp_path / "empty"
     empty.mkdir()
-    ring = io.tfio_ring_open(str(empty).encode(), 3, 0, -1, 1)
+    ring = io.tfio_ring_open(str(empty).encode(), 3, 0, -1, 1, 2)
     try:
         assert drain(io, ring) == [] and b"0000.pgm" in io.tfio_ring_error(ring)
     finally:
@@ -178,8 +179,8 @@ def test_ring_fails_loudly_without_page_locked_memory(io, tmp_path):
     if has_cuda():
         pytest.skip("a CUDA device is present: page-locking works")
     write_pgm(str(tmp_path / "0000.pgm"), np.zeros((4, 4), np.uint16))
-    assert io.tfio_ring_open(str(tmp_path).encode(), 3, 0, -1, 0) is None
-    ring = io.tfio_ring_open(str(tmp_path).encode(), 3, 0, -1, 1)
+    assert io.tfio_ring_open(str(tmp_path).encode(), 3, 0, -1, 0, 2) is None
+    ring = io.tfio_ring_open(str(tmp_path).encode(), 3, 0, -1, 1, 2)
     assert ring and io.tfio_ring_pinned(ring) == 0
     io.tfio_ring_close(ring)
 
