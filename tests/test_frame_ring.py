@@ -204,3 +204,22 @@ def test_demo_with_the_ring_equals_the_synchronous_demo(gpu, tmp_path):
         outs.append((re.findall(r"frame\s+\d+ ok=\d t=\([^)]*\) voxel-updates=\d+", r.stdout), open(view, "rb").read(), r.stdout))
     assert len(outs[0][0]) == 8 and outs[0][0] == outs[1][0] and outs[0][1] == outs[1][1]
     assert "page-locked memory" in outs[1][2]
+
+
+def test_ring_is_race_free(tmp_path):
+    """src/frame_ring.cpp under ThreadSanitizer: 1-4 decoder threads against a consumer that holds frames, and an early close"""
+    import shutil
+    import subprocess
+    cxx = shutil.which("g++")
+    if not cxx:
+        pytest.skip("no g++")
+    exe = str(tmp_path / "ring_tsan")
+    b = subprocess.run([cxx, "-std=c++17", "-O1", "-g", "-fsanitize=thread", "-I" + os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "tests", "cpp", "frame_ring_tsan.cpp"), os.path.join(ROOT, "src", "frame_ring.cpp"),
+                        "-o", exe, "-lpthread"], capture_output=True, text=True, timeout=300)
+    if b.returncode != 0 and "tsan" in b.stderr.lower():
+        pytest.skip("ThreadSanitizer runtime not installed")
+    assert b.returncode == 0, b.stderr[-2000:]
+    frames = tmp_path / "frames"
+    r = subprocess.run([exe, str(frames)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "bad = 0" in r.stdout and "ThreadSanitizer" not in r.stderr, r.stdout + r.stderr[-3000:]
