@@ -14,3 +14,8 @@ echo "ncu list rc=$?"
 $CMD > gpurun_out/plain_$TAG.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:"k_icp_all|k_integrate$|k_raycast|k_bilateral|k_mark|k_visible_list|k_model_maps|k_pyr_maps" -s 16 -c 16 -f -o gpurun_out/prof_$TAG $CMD > gpurun_out/ncu_f_$TAG.log 2>&1
 echo "ncu full rc=$?"
+# the sharded kernels on ONE GPU (two emulated ranks: every peer access is local) — the only legitimate way to put ncu on them
+CMD2="python tools/profile_sharded_emulated.py --frames 16"
+$CMD2 > gpurun_out/shard_emul_$TAG.json 2> gpurun_out/shard_emul_$TAG.err &&
+ncu --set full --clock-control none --import-source on -k regex:"k_raycast_sharded|k_gather_foreign" -s 24 -c 4 -f -o gpurun_out/prof_shard_emul_$TAG $CMD2 > gpurun_out/ncu_shard_emul_$TAG.log 2>&1
+echo "ncu sharded (emulated) rc=$?"
