@@ -169,9 +169,24 @@ def algorithmic_bytes(kernel: str, cols: int, rows: int, n_vis_alloc: float) -> 
     return None
 
 
+def _use_all_host_threads() -> int:
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm must use every host core at every N (round-1 SCALE runs
+    timed a single-threaded baseline).  Set before libgomp is loaded, and again through its API in case it already was."""
+    n = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    os.environ.pop("OMP_THREAD_LIMIT", None)
+    try:
+        import ctypes
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(n)
+    except OSError:
+        pass
+    return n
+
+
 def cpu_oracle_run(frames, mode: int, warmup: int):
     """the reference's algorithm on the host cores: oracle/_ref (the reference's own per-pixel / per-voxel functions
     compiled where they lie + restated imgproc/ICP) when it was built, else the oracle port"""
+    threads = _use_all_host_threads()
     from oracle import tfo
     kind = "reference" if tfo.have_ref() else "port"
     L = tfo.Lib("ref" if kind == "reference" else "port")
@@ -186,7 +201,7 @@ def cpu_oracle_run(frames, mode: int, warmup: int):
     dt = time.perf_counter() - t0
     n = len(frames) - warmup
     o.close()
-    return {"value": n / dt, "unit": "frames/s", "cores": os.cpu_count(), "kind": kind,
+    return {"value": n / dt, "unit": "frames/s", "cores": threads, "kind": kind,
             "sample": f"{n} consecutive S1 frames after {warmup} warm-up frames, same mode and parameters; "
                       + ("oracle/_ref: the reference's own host-compilable per-pixel/per-voxel functions driven by OpenMP "
                          "host loops + restated imgproc/ICP (the reference has no CPU engine)" if kind == "reference"
@@ -290,6 +305,60 @@ def ingest_leg(frames, mode, n_warm=10):
         finally:
             shutil.rmtree(d, ignore_errors=True)
     except Exception as e:   # noqa: BLE001 — an extra leg must never cost the headline
+        return {"error": "%s: %s" % (type(e).__name__, e)}
+
+
+def reference_gpu_leg(n_frames=100, n_warm=5):
+    """GPU-vs-GPU anchor: the reference library's OWN GPU path — /root/reference/tfusion patched
+    only as far as baseline/ref_gpu/patch_ref.py lists so that it compiles for sm_100a, with the reference's nvcc flags — on the
+    same B200, same S1 frames, driven as apps/demo.cpp drives it (host frame -> upload -> operator()), wall clock.  Two builds:
+    as shipped (its per-frame debug downloads, pose print and extra render left in) and with that debug work
+    removed.  The reference only has its own tracking behaviour (the estimate runs away and the scene is reset every
+    ~9 frames on this orbit), so this repo's path is timed beside it in the SAME mode on the same frames through
+    tfb_process_frame from host memory.  Never allowed to fail the bench line."""
+    try:
+        from baseline.ref_gpu import refgpu
+        if not (refgpu.available("nodebug") and refgpu.available("asis")):
+            return {"unavailable": "baseline/_ref/libref_gpu*.so not built (make -C baseline/ref_gpu where /root/reference exists)"}
+        from topfusion_b200 import capi
+        frames, _ = orbit_frames(n_frames)
+        out = {"what": "3d-scan/topfusion reference GPU path, patched to compile (baseline/ref_gpu/patch_ref.py), same B200",
+               "frames": n_frames - n_warm, "unit": "frames/s", "mode": "reference (the only mode the reference has)",
+               "timing": "wall clock around the loop, host frames, upload inside, first %d frames excluded; best of 2 runs" % n_warm}
+        for variant, key in (("nodebug", "debug_work_removed"), ("asis", "as_shipped")):
+            best, tracked = 0.0, 0
+            for _ in range(2):
+                R = refgpu.RefTopFu(variant=variant)
+                for i in range(n_warm):
+                    R.frame(frames[i])
+                R.sync(); t0 = time.perf_counter(); oks = 0
+                for i in range(n_warm, n_frames):
+                    oks += R.frame(frames[i])
+                R.sync(); fps = (n_frames - n_warm) / (time.perf_counter() - t0)
+                R.close()
+                if fps > best:
+                    best, tracked = fps, oks
+            out[key] = {"value": best, "frames_tracked": tracked}
+        best, tracked = 0.0, 0
+        import ctypes as C
+        for _ in range(2):
+            ctx = capi.Context(corrected_mode=0)
+            okv = C.c_int(0)
+            for i in range(n_warm):
+                ctx.process_frame(frames[i])
+            ctx.sync(); t0 = time.perf_counter(); oks = 0
+            for i in range(n_warm, n_frames):
+                ctx._ck(ctx.L.tfb_process_frame(ctx.h, frames[i].ctypes.data_as(C.c_void_p), C.c_size_t(frames.shape[2] * 2), C.byref(okv)))
+                oks += okv.value
+            ctx.sync(); fps = (n_frames - n_warm) / (time.perf_counter() - t0)
+            ctx.close()
+            if fps > best:
+                best, tracked = fps, oks
+        out["this_repo_same_mode_same_frames"] = {"value": best, "frames_tracked": tracked}
+        out["speedup_vs_debug_work_removed"] = best / out["debug_work_removed"]["value"]
+        out["speedup_vs_as_shipped"] = best / out["as_shipped"]["value"]
+        return out
+    except Exception as e:   # noqa: BLE001
         return {"error": "%s: %s" % (type(e).__name__, e)}
 
 
@@ -441,6 +510,7 @@ def main():
     from topfusion_b200 import multigpu
     large = multigpu.integrate_scaling_leg(0, 1)
     ingest = ingest_leg(frames[:min(W + K, 100)], args.mode)
+    ref_gpu = reference_gpu_leg()
 
     # the same frame path in REFERENCE mode (bug for bug): the estimate runs away and operator() resets the
     # scene every ~10 frames on the hover sequence and every ~7 on the orbit — reported beside the headline, labelled
@@ -471,6 +541,7 @@ def main():
         "voxel_updates_large_scene": large,
         "other_modes": other,
         "ingest_from_files": ingest,
+        "reference_gpu": ref_gpu,
         "warm_l2_value": K / (warm_ms / 1000.0),
         "kernels": table,
         "bandwidth_kernels": extra,

@@ -43,6 +43,7 @@ template <typename T, int n> struct Vec {
     static Vec all(T v) { Vec r; for (int i = 0; i < n; ++i) r.val[i] = v; return r; }
     T& operator[](int i) { return val[i]; }
     const T& operator[](int i) const { return val[i]; }
+    template <typename T2> operator Vec<T2, n>() const { Vec<T2, n> r; for (int i = 0; i < n; ++i) r.val[i] = (T2)val[i]; return r; }   // OpenCV: Matx::operator Matx<T2,m,n>()
 };
 template <typename T, int n> inline Vec<T, n> operator/(const Vec<T, n>& a, T s) { Vec<T, n> r; for (int i = 0; i < n; ++i) r[i] = a[i] / s; return r; }
 typedef Vec<float, 3> Vec3f;
@@ -70,6 +71,7 @@ template <typename T> struct Affine3 {
         for (int i = 0; i < 3; ++i) matrix(i, 3) = t[i];
     }
     static Affine3 Identity() { return Affine3(); }
+    template <typename Y> operator Affine3<Y>() const { Affine3<Y> r; for (int i = 0; i < 16; ++i) r.matrix.val[i] = (Y)matrix.val[i]; return r; }   // affine.hpp: cast to another element type
     Mat3 rotation() const { Mat3 r; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) r(i, j) = matrix(i, j); return r; }
     Vec3 translation() const { return Vec3(matrix(0, 3), matrix(1, 3), matrix(2, 3)); }
     Affine3 translate(const Vec3& t) const { Affine3 r(*this); for (int i = 0; i < 3; ++i) r.matrix(i, 3) += t[i]; return r; }

@@ -66,6 +66,8 @@ struct KF_EXPORTS TopFuSceneConfig {
     bool print_pose = false;      // the reference prints the pose every frame (topfu.cpp:252)
     bool defer_tail = true;       // operator() returns once the pose is known; integration / raycast of that frame run beside the
                                   // next frame's preprocessing (or before anything looks at the scene).  Results are identical.
+    bool ieee_arith = false;      // TSDF integration: false = the arithmetic of the reference's GPU build (bit-identical voxels to the
+                                  // reference on the same GPU); true = IEEE, bit-identical to a host compile of the same function
 };
 
 class KF_EXPORTS TopFu {

@@ -66,6 +66,11 @@ typedef struct tfb_params {
                                      * integration, raycast and model maps of that frame are enqueued by the next call (beside
                                      * its preprocessing, on a second stream) or by any call that looks at the scene.  0: the
                                      * whole frame is finished before the call returns.  Results are identical. */
+    int32_t ieee_arith;             /* TSDF integration arithmetic.  0 (default): the arithmetic of the reference's own GPU
+                                     * build (tfusion/CMakeLists.txt:1: --ftz=true --prec-div=false, fused multiply-adds) —
+                                     * every voxel bit-identical to what the reference's integrateIntoScene_device writes on
+                                     * the same GPU.  1: IEEE evaluation without contraction — every voxel bit-identical to a
+                                     * HOST compile of computeUpdatedVoxelDepthInfo (the CPU oracle).  DESIGN.md section 4. */
 } tfb_params;
 
 typedef struct tfb_ctx tfb_ctx;

@@ -28,7 +28,7 @@ def test_config3_room_1280x720_stages_bit_exact(gpu):
               num_blocks=1 << 18, num_buckets=1 << 22, excess_size=1 << 18, depth_cutoff_mm=4000, view_frustum_max=4.0)
     L = tfo.Lib("port")
     o = tfo.Oracle(lib=L, **kw)
-    g = gpu.Context(**kw)
+    g = gpu.Context(ieee_arith=1, **kw)
     try:
         for i in range(3):
             dists = L.compute_dists(depth[i], 4000)
@@ -65,7 +65,7 @@ def test_config3_room_1280x720_tracked_frames(gpu):
               num_blocks=1 << 18, num_buckets=1 << 22, excess_size=1 << 18, depth_cutoff_mm=4000, view_frustum_max=4.0,
               icp_truncate_depth_dist=4.0, corrected_mode=1)
     o = tfo.Oracle(**kw)
-    g = gpu.Context(**kw)
+    g = gpu.Context(ieee_arith=1, **kw)
     try:
         for i in range(4):
             ok_o, ok_g = o.process_frame(depth[i]), g.process_frame(depth[i])

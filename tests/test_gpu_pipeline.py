@@ -18,7 +18,7 @@ def _rot_angle(Ra, Rb):
 def _run(gpu, depth, n, **kw):
     from oracle import tfo
     o = tfo.Oracle(**kw)
-    g = gpu.Context(**kw)
+    g = gpu.Context(ieee_arith=1, **kw)
     rows = []
     for i in range(n):
         ok_o = o.process_frame(depth[i])
@@ -110,7 +110,7 @@ def test_reset_after_tracking_loss(gpu, s1_frames):
     from oracle import tfo
     depth, _, _ = s1_frames
     o = tfo.Oracle()
-    g = gpu.Context()
+    g = gpu.Context(ieee_arith=1)
     try:
         blank = np.zeros_like(depth[0])
         seq = [depth[0], depth[1], blank, depth[2], depth[3]]
@@ -126,7 +126,7 @@ def test_reset_after_tracking_loss(gpu, s1_frames):
 
 def test_pinned_and_strided_input(gpu, s1_frames):
     depth, _, _ = s1_frames
-    g1, g2 = gpu.Context(), gpu.Context()
+    g1, g2 = gpu.Context(ieee_arith=1), gpu.Context(ieee_arith=1)
     try:
         pin = gpu.PinnedArray((480, 704), np.uint16)   # row stride larger than the image (cv::Mat step)
         for i in range(3):
@@ -145,7 +145,7 @@ def test_pinned_and_strided_input(gpu, s1_frames):
 
 def test_gpu_launch_counter_and_timing(gpu, s1_frames):
     depth, _, _ = s1_frames
-    g = gpu.Context()
+    g = gpu.Context(ieee_arith=1)
     try:
         g.timing(True)
         n0 = g.kernel_launches()
@@ -161,14 +161,15 @@ def test_gpu_launch_counter_and_timing(gpu, s1_frames):
 def test_against_committed_golden_vectors(gpu):
     """the CUDA path against tests/golden/*.npz (written from the reference-backed oracle/_ref build)"""
     import glob, os
-    paths = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+    paths = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
+                   if not os.path.basename(p).startswith("refgpu_"))   # those come from the reference's GPU build: test_gpu_refgpu_fixtures.py
     assert paths
     for path in paths:
         z = np.load(path)
         mode, voxel, mu = z["params"]
         intr = z["intr"]
         rows, cols = z["depth"].shape[1:]
-        g = gpu.Context(cols=cols, rows=rows, fx=float(intr[0]), fy=float(intr[1]), cx=float(intr[2]), cy=float(intr[3]),
+        g = gpu.Context(cols=cols, rows=rows, fx=float(intr[0]), fy=float(intr[1]), cx=float(intr[2]), cy=float(intr[3]), ieee_arith=1,
                         corrected_mode=int(mode), voxel_size=float(voxel), mu=float(mu))
         try:
             for i in range(len(z["depth"])):
@@ -226,7 +227,7 @@ def test_blank_first_frame_then_tracking(gpu, s1_frames):
     from oracle import tfo
     depth, _, _ = s1_frames
     o = tfo.Oracle(corrected_mode=1)
-    g = gpu.Context(corrected_mode=1)
+    g = gpu.Context(corrected_mode=1, ieee_arith=1)
     try:
         seq = [np.zeros_like(depth[0]), depth[0], depth[1], depth[2]]
         for i, d in enumerate(seq):

@@ -13,7 +13,7 @@ def _run_both(gpu, tfo, depth, poses, n, **kw):
     """alloc+integrate+expected-depth+icp-maps for n frames with ground-truth poses on both sides"""
     L = tfo.Lib("port")
     o = tfo.Oracle(lib=L, **kw)
-    g = gpu.Context(**kw)
+    g = gpu.Context(ieee_arith=1, **kw)   # IEEE arithmetic: the CPU oracle is a host compile of the reference
     out = []
     for i in range(n):
         dists = L.compute_dists(depth[i], o.params.depth_cutoff_mm)
@@ -146,7 +146,7 @@ def test_other_voxel_sizes_incl_knife_edges(gpu, s1_frames, voxel, mu):
 
 
 def test_empty_frame_allocates_nothing(gpu):
-    g = gpu.Context()
+    g = gpu.Context(ieee_arith=1)
     try:
         z = np.full((480, 640), -1.0, np.float32)
         g.allocate(np.eye(4, dtype=np.float32), z)
@@ -162,7 +162,7 @@ def test_pool_exhaustion_restores_counters(gpu, s1_frames):
     from oracle import tfo
     depth, poses, _ = s1_frames
     L = tfo.Lib("port")
-    g = gpu.Context(num_blocks=500)
+    g = gpu.Context(num_blocks=500, ieee_arith=1)
     try:
         dists = L.compute_dists(depth[0])
         for _ in range(2):

@@ -24,10 +24,10 @@ def peak():
         return 6650.0
 
 
-def run(capi, depth, poses, intr, voxel, mu, frames, warm, flush, depth_cutoff_mm):
+def run(capi, depth, poses, intr, voxel, mu, frames, warm, flush, depth_cutoff_mm, ieee=0):
     rows, cols = depth.shape[1:]
     ctx = capi.Context(cols=cols, rows=rows, fx=intr[0], fy=intr[1], cx=intr[2], cy=intr[3], voxel_size=voxel, mu=mu,
-                       num_blocks=1 << 20, num_buckets=1 << 22, excess_size=1 << 19, depth_cutoff_mm=depth_cutoff_mm,
+                       num_blocks=1 << 20, num_buckets=1 << 22, excess_size=1 << 19, depth_cutoff_mm=depth_cutoff_mm, ieee_arith=ieee,
                        view_frustum_max=max(3.0, depth_cutoff_mm / 1000.0 + 2 * mu))
     L = ctx.L
     n = depth.shape[0]
@@ -67,7 +67,7 @@ def run(capi, depth, poses, intr, voxel, mu, frames, warm, flush, depth_cutoff_m
     alg = {"k_integrate": nb * 4116.0 + 4.0 * p0, "k_raycast": p0 * 16.0 + p0 / 64.0 * 8.0 + nb * 2064.0, "k_icp_maps": p0 * 48.0,
            "k_mark": 4.0 * p0 + 16.0 * nb, "k_expected_depths": 36.0 * nb}
     out = {"voxel_mm": voxel * 1000, "mu_mm": mu * 1000, "cols": cols, "rows": rows, "visible_blocks_avg": nb,
-           "allocated": cnt["n_allocated"], "l2_flushed": bool(flush), "kernels": {}}
+           "allocated": cnt["n_allocated"], "l2_flushed": bool(flush), "ieee_arith": int(ieee), "kernels": {}}
     pk = peak()
     for k, (ms, launches) in kt.items():
         us = 1000.0 * ms / launches
@@ -91,6 +91,7 @@ def main():
     ap.add_argument("--seq-frames", type=int, default=40)
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--out", default=None)
+    ap.add_argument("--ieee", type=int, default=0, help="1: IEEE integration arithmetic (tfb_params.ieee_arith)")
     a = ap.parse_args()
     from topfusion_b200 import capi, synth
     depth, poses, intr = synth.sequence(a.seq, a.seq_frames)
@@ -98,7 +99,7 @@ def main():
     res = []
     for v in a.voxel_mm:
         for m in a.mu_voxels:
-            r = run(capi, depth, poses, intr, v / 1000.0, m * v / 1000.0, a.frames, a.warmup, not a.no_flush, cutoff)
+            r = run(capi, depth, poses, intr, v / 1000.0, m * v / 1000.0, a.frames, a.warmup, not a.no_flush, cutoff, a.ieee)
             res.append(r)
             ki, kr = r["kernels"]["k_integrate"], r["kernels"]["k_raycast"]
             print(f"{a.seq} voxel {v} mm mu {m * v} mm: {r['visible_blocks_avg']:.0f} blocks | integrate {ki['us_per_launch']:.1f} us "

@@ -36,6 +36,7 @@ class Params(C.Structure):
         ("depth_cutoff_mm", C.c_int32), ("corrected_mode", C.c_int32),
         ("shard_rank", C.c_int32), ("shard_count", C.c_int32),
         ("defer_tail", C.c_int32),
+        ("ieee_arith", C.c_int32),
     ]
 
 

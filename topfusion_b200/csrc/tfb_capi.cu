@@ -421,6 +421,7 @@ int tfb_default_params(tfb_params* p) {
     p->depth_cutoff_mm = 2047;
     p->corrected_mode = 0; p->shard_rank = 0; p->shard_count = 1;
     p->defer_tail = 1;
+    p->ieee_arith = 0;
     return TFB_OK;
 }
 
