@@ -11,7 +11,15 @@ WANT = ["Kernel Name", "launch__grid_size", "launch__block_size", "launch__regis
         "l1tex__t_sector_hit_rate.pct", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "smsp__average_warp_latency_per_inst_issued.ratio", "smsp__thread_inst_executed_per_inst_executed.ratio",
-        "launch__waves_per_multiprocessor", "launch__occupancy_limit_registers", "launch__occupancy_limit_warps"]
+        "launch__waves_per_multiprocessor", "launch__occupancy_limit_registers", "launch__occupancy_limit_warps",
+        "smsp__inst_executed.sum", "sm__inst_executed_pipe_xu.sum", "sm__inst_executed_pipe_fma.sum", "sm__inst_executed_pipe_alu.sum",
+        "sm__inst_executed_pipe_lsu.sum", "sm__pipe_xu_cycles_active.avg.pct_of_peak_sustained_active",
+        "lts__t_sectors_op_atom.sum", "lts__t_sectors_op_red.sum", "l1tex__t_set_accesses_pipe_lsu_mem_global_op_atom.sum",
+        "l1tex__t_set_accesses_pipe_lsu_mem_global_op_red.sum", "lts__t_bytes.sum", "l1tex__t_bytes.sum",
+        "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct", "smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct",
+        "smsp__warp_issue_stalled_math_pipe_throttle_per_warp_active.pct", "smsp__warp_issue_stalled_barrier_per_warp_active.pct",
+        "smsp__warp_issue_stalled_wait_per_warp_active.pct", "smsp__warp_issue_stalled_not_selected_per_warp_active.pct",
+        "smsp__warp_issue_stalled_lg_throttle_per_warp_active.pct", "smsp__warp_issue_stalled_branch_resolving_per_warp_active.pct"]
 
 
 def main(rep, out):

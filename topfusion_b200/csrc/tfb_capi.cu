@@ -25,6 +25,35 @@ int used_levels(const tfb_params& p) {  // ProjectiveICP::getUsedLevelsNum, proj
     return i + 1;
 }
 
+// k_icp_all stamps its partial rows with an epoch that is unique per (launch, iteration): 64 epochs are reserved per launch
+// (tfb_icp.cu), so a coarse-to-fine loop may have at most 63 iterations in total — more would let a late row of one launch
+// pass for an early row of the next.  The reference's default is 19.
+bool icp_iters_ok(const int iters[4]) {
+    int total = 0;
+    for (int i = 0; i < 4; ++i) {
+        if (iters[i] < 0) return false;
+        total += iters[i];
+    }
+    return total <= 63;
+}
+
+// k_mark encodes (pixel, step) of the winning request in one 32-bit claim key with 6 bits of step (tfb_scene.cu), i.e. at most
+// 64 samples along a ray's +-mu segment; buildHashAllocAndVisibleTypePP takes ceil(2 * |segment| / block) of them.  The longest
+// segment belongs to the pixel farthest from the principal point.
+bool alloc_steps_ok(const tfb_params& p) {
+    float worst = 0.f;
+    const float xs[2] = {0.f, (float)(p.cols - 1)}, ys[2] = {0.f, (float)(p.rows - 1)};
+    for (float x : xs)
+        for (float y : ys) {
+            const float dx = (x - p.cx) / p.fx, dy = (y - p.cy) / p.fy;
+            const float f = sqrtf(dx * dx + dy * dy + 1.f);
+            worst = f > worst ? f : worst;
+        }
+    const float len = worst * 2.f * p.mu / (p.voxel_size * 8.f);
+    const long long pixels = (long long)p.cols * p.rows;
+    return ceilf(2.f * len) + 1.f <= 64.f && pixels < (1ll << 26);   // 26 bits of pixel index beside the 6 bits of step
+}
+
 template <typename T>
 cudaError_t dmalloc(T** p, size_t n) { return cudaMalloc((void**)p, n * sizeof(T)); }
 
@@ -353,6 +382,9 @@ int do_frame(tfb_ctx* c, const uint16_t* depth, size_t host_step_bytes, int* ok,
                     if (q == cudaSuccess && *seq != want) return set_err(c, TFB_ERR_STATE, "ICP kernel finished without publishing its state");
                 }
             }
+            // the state block was written before the sequence word (system fence on the device side); the loads of pose,
+            // verdict and counters below must not be satisfied before the load that saw the sequence word
+            __atomic_thread_fence(__ATOMIC_ACQUIRE);
         }
     } else {
         stamp(c, ST_FRAME);
@@ -432,6 +464,7 @@ int tfb_create(const tfb_params* p, void* stream, tfb_ctx** out) {
     if (p->num_buckets <= 0 || (p->num_buckets & (p->num_buckets - 1))) return TFB_ERR_ARG;
     if (p->num_blocks <= 0 || p->excess_size <= 0 || p->voxel_size <= 0 || p->mu <= 0) return TFB_ERR_ARG;
     if (p->shard_count < 1 || p->shard_count > TFB_MAX_SHARDS || p->shard_rank < 0 || p->shard_rank >= p->shard_count) return TFB_ERR_ARG;
+    if (!icp_iters_ok(p->icp_iters) || !alloc_steps_ok(*p)) return TFB_ERR_ARG;   // fixed-width encodings, see the two helpers
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return TFB_ERR_CUDA;  // no CPU fallback, by design
 
@@ -707,6 +740,12 @@ int tfb_icp_estimate_ext(tfb_ctx* c, int levels, const float* const* vcurr, cons
                          const float* const* nprev, int cols, int rows, const int* iters, float dist_thres, float angle_thres,
                          const float intr_or_null[4], float affine_out[16], int* ok) {
     if (!c || !vcurr || !ncurr || !vprev || !nprev || !iters || !affine_out || !ok) return TFB_ERR_ARG;
+    if (levels < 1 || levels > MAX_LEVELS) return set_err(c, TFB_ERR_ARG, "tfb_icp_estimate_ext: 1..4 pyramid levels");
+    {
+        int it4[4] = {0, 0, 0, 0};
+        for (int i = 0; i < levels; ++i) it4[i] = iters[i];
+        if (!icp_iters_ok(it4)) return set_err(c, TFB_ERR_ARG, "tfb_icp_estimate_ext: iteration counts must be >= 0 and sum to at most 63");
+    }
     TFB_SETTLE(c);
     tfb_params saved = c->p;
     if (intr_or_null) { c->p.fx = intr_or_null[0]; c->p.fy = intr_or_null[1]; c->p.cx = intr_or_null[2]; c->p.cy = intr_or_null[3]; }
@@ -721,6 +760,7 @@ int tfb_icp_estimate_ext(tfb_ctx* c, int levels, const float* const* vcurr, cons
 
 int tfb_set_icp_params(tfb_ctx* c, float dist_thres, float angle_thres, const int iters[4]) {
     if (!c || !iters) return TFB_ERR_ARG;
+    if (!icp_iters_ok(iters)) return set_err(c, TFB_ERR_ARG, "tfb_set_icp_params: iteration counts must be >= 0 and sum to at most 63");
     tfb_params q = c->p;
     for (int i = 0; i < 4; ++i) q.icp_iters[i] = iters[i];
     if (used_levels(q) > MAX_LEVELS || used_levels(q) < 1) return TFB_ERR_ARG;

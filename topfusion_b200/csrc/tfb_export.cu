@@ -10,6 +10,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <new>
 #include <vector>
 
 #include "tfb_common.cuh"
@@ -142,6 +143,7 @@ int tfb_extract_points(tfb_ctx* c, float* points_dev, int capacity, int* n_out) 
 // ---- scene file ------------------------------------------------------------------------------------------
 // header: magic, version, voxel_size, mu, num_buckets, excess_size, n_blocks, n_poses; then n_poses x 16 floats;
 // then n_blocks x { short pos[3], pad; 512 x u32 voxels }.  The hash geometry of the loading context must match.
+constexpr int MAX_FILE_POSES = 1 << 24;   // 1 GB of poses: anything above is a corrupt header, not a trajectory
 struct SceneFileHeader {
     char magic[8];
     int32_t version;
@@ -149,8 +151,7 @@ struct SceneFileHeader {
     int32_t num_buckets, excess_size, n_blocks, n_poses;
 };
 
-int tfb_scene_save(tfb_ctx* c, const char* path) {
-    if (!c || !path) return TFB_ERR_ARG;
+static int scene_save_impl(tfb_ctx* c, const char* path) {
     int r = tfb_sync(c);
     if (r) return r;
     std::vector<HashEntry> table((size_t)c->total_entries);
@@ -179,8 +180,19 @@ int tfb_scene_save(tfb_ctx* c, const char* path) {
     return ok ? TFB_OK : set_err(c, TFB_ERR_CUDA, "tfb_scene_save: write failed");
 }
 
-int tfb_scene_load(tfb_ctx* c, const char* path) {
+// std::vector may throw; nothing may leave an extern "C" function
+int tfb_scene_save(tfb_ctx* c, const char* path) {
     if (!c || !path) return TFB_ERR_ARG;
+    try {
+        return scene_save_impl(c, path);
+    } catch (const std::bad_alloc&) {
+        return set_err(c, TFB_ERR_NOMEM, "tfb_scene_save: out of host memory");
+    } catch (...) {
+        return set_err(c, TFB_ERR_STATE, "tfb_scene_save: unexpected failure");
+    }
+}
+
+static int scene_load_impl(tfb_ctx* c, const char* path) {
     if (c->p.shard_count > 1) return set_err(c, TFB_ERR_STATE, "tfb_scene_load: not for a sharded context");
     FILE* f = fopen(path, "rb");
     if (!f) return set_err(c, TFB_ERR_ARG, "tfb_scene_load: cannot open the file");
@@ -190,9 +202,19 @@ int tfb_scene_load(tfb_ctx* c, const char* path) {
         return set_err(c, TFB_ERR_ARG, "tfb_scene_load: not a scene file");
     }
     if (h.num_buckets != c->p.num_buckets || h.excess_size != c->p.excess_size || h.voxel_size != c->p.voxel_size || h.mu != c->p.mu ||
-        h.n_blocks > c->p.num_blocks || h.n_poses < 1) {
+        h.n_blocks < 0 || h.n_blocks > c->p.num_blocks || h.n_poses < 1 || h.n_poses > MAX_FILE_POSES) {
         fclose(f);
-        return set_err(c, TFB_ERR_ARG, "tfb_scene_load: the file was written with a different voxel size / band / hash geometry");
+        return set_err(c, TFB_ERR_ARG, "tfb_scene_load: the file was written with a different voxel size / band / hash geometry, or its header is corrupt");
+    }
+    {   // the header must describe exactly the bytes that follow: sizes below are taken from it
+        const long long want = (long long)sizeof(h) + (long long)h.n_poses * 64 + (long long)h.n_blocks * (8 + (long long)BLOCK3 * 4);
+        long long have = -1;
+        const long here = ftell(f);
+        if (here >= 0 && fseek(f, 0, SEEK_END) == 0) { have = ftell(f); fseek(f, here, SEEK_SET); }
+        if (have != want) {
+            fclose(f);
+            return set_err(c, TFB_ERR_ARG, "tfb_scene_load: file size does not match its header");
+        }
     }
     std::vector<float> poses((size_t)h.n_poses * 16);
     bool ok = fread(poses.data(), 16 * sizeof(float), (size_t)h.n_poses, f) == (size_t)h.n_poses;
@@ -212,10 +234,13 @@ int tfb_scene_load(tfb_ctx* c, const char* path) {
         if (!ok) break;
         const int ptr = last_free_block--;   // vba_free is the identity permutation after a reset
         int slot = (int)((((unsigned)(int)pos[0] * 73856093u) ^ ((unsigned)(int)pos[1] * 19349669u) ^ ((unsigned)(int)pos[2] * 83492791u)) & (unsigned)mask);
+        auto same = [&](int s_) { return table[s_].pos[0] == pos[0] && table[s_].pos[1] == pos[1] && table[s_].pos[2] == pos[2]; };
         if (table[slot].ptr < -1) {
             bits[slot >> 5] |= 1u << (slot & 31);
         } else {
-            while (table[slot].offset >= 1) slot = nbk + table[slot].offset - 1;
+            bool dup = same(slot);
+            while (!dup && table[slot].offset >= 1) { slot = nbk + table[slot].offset - 1; dup = same(slot); }
+            if (dup) { fclose(f); return set_err(c, TFB_ERR_ARG, "tfb_scene_load: a block position occurs twice in the file"); }
             if (last_free_excess < 0) { ok = false; break; }
             const int off = last_free_excess--;   // excess_free is the identity permutation after a reset
             table[slot].offset = off + 1;
@@ -272,6 +297,17 @@ int tfb_scene_load(tfb_ctx* c, const char* path) {
     if ((r = launch_model_maps(c))) return r;
     TFB_CUDA(c, cudaStreamSynchronize(c->stream));
     return TFB_OK;
+}
+
+int tfb_scene_load(tfb_ctx* c, const char* path) {
+    if (!c || !path) return TFB_ERR_ARG;
+    try {
+        return scene_load_impl(c, path);
+    } catch (const std::bad_alloc&) {
+        return set_err(c, TFB_ERR_NOMEM, "tfb_scene_load: out of host memory");
+    } catch (...) {
+        return set_err(c, TFB_ERR_STATE, "tfb_scene_load: unexpected failure");
+    }
 }
 
 }  // extern "C"

@@ -806,6 +806,7 @@ int launch_icp_all(tfb_ctx* c, bool update_pose) {
 
 static int launch_icp_args(tfb_ctx* c, IcpAllArgs& a, int total) {
     if (total == 0) return TFB_OK;
+    if (total > 63) return set_err(c, TFB_ERR_ARG, "icp: more than 63 iterations in one coarse-to-fine loop (64 row epochs per launch)");
     if (c->icp_grid == 0) {
         int per_sm = 0, sms = 0;
         TFB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_icp_all, ICPA_THREADS, 0));
