@@ -52,13 +52,13 @@ def test_reference_demo_runs_on_this_repos_library(gpu, tmp_path):
                TFUSION_STUB_VIEW_OUT=str(tmp_path / "view.raw"))
     r = subprocess.run([BIN], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=180)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    poses = np.loadtxt(tmp_path / "poses.txt").reshape(-1, 4, 4)
+    poses = np.loadtxt(tmp_path / "poses.txt").reshape(-1, 4, 4).astype(np.float32)   # %.9g round-trips a float exactly
     assert len(poses) == n
     g = gpu.Context()          # TopFuParams::default_params() == tfb_default_params(): reference behaviour
     try:
         for i in range(n):
             g.process_frame(depth[i])
-            assert np.array_equal(g.pose().astype(np.float64), poses[i]), i
+            assert np.array_equal(g.pose(), poses[i]), i
         view = np.fromfile(tmp_path / "view.raw", np.uint8).reshape(480, 640, 4)
         assert np.array_equal(view, g.render_image())
         assert view[..., 0].max() > 0

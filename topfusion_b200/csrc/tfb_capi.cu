@@ -51,7 +51,7 @@ bool alloc_steps_ok(const tfb_params& p) {
         }
     const float len = worst * 2.f * p.mu / (p.voxel_size * 8.f);
     const long long pixels = (long long)p.cols * p.rows;
-    return ceilf(2.f * len) + 1.f <= 64.f && pixels < (1ll << 26);   // 26 bits of pixel index beside the 6 bits of step
+    return ceilf(2.f * len) + 1.f <= 64.f && pixels < (1ll << 23);   // 26 bits of pixel index beside the 6 bits of step; k_integrate forms the index exactly in fp32 (2^23)
 }
 
 template <typename T>
