@@ -89,7 +89,7 @@ def test_config4_large_scene_2mm_sharded_bit_exact(gpu):
     kw = dict(voxel_size=0.002, mu=0.008, num_blocks=1 << 19, num_buckets=1 << 22, excess_size=1 << 18, depth_cutoff_mm=4000)
     L = tfo.Lib("port")
     o = tfo.Oracle(lib=L, **kw)
-    ctxs = make_shards(gpu, 2, **kw)
+    ctxs = make_shards(gpu, 2, ieee_arith=1, **kw)   # the oracle is a host compile of the reference: IEEE arithmetic
     try:
         for i in range(2):
             dists = L.compute_dists(depth[i], 4000)
