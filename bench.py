@@ -509,6 +509,7 @@ def main():
 
     from topfusion_b200 import multigpu
     large = multigpu.integrate_scaling_leg(0, 1)
+    large_720p = multigpu.integrate_scaling_leg(0, 1, frames=16, cols=1280, rows=720)
     ingest = ingest_leg(frames[:min(W + K, 100)], args.mode)
     ref_gpu = reference_gpu_leg()
 
@@ -539,6 +540,7 @@ def main():
         "cpu_baseline": cpu,
         "voxel_updates_per_s": vox / (total_ms / 1000.0),
         "voxel_updates_large_scene": large,
+        "voxel_updates_large_scene_1280x720": large_720p,
         "other_modes": other,
         "ingest_from_files": ingest,
         "reference_gpu": ref_gpu,

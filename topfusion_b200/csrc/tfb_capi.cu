@@ -59,7 +59,7 @@ cudaError_t dmalloc(T** p, size_t n) { return cudaMalloc((void**)p, n * sizeof(T
 
 void free_all(tfb_ctx* c) {
     cudaFree(c->table); cudaFree(c->vba); cudaFree(c->vba_free); cudaFree(c->excess_free);
-    cudaFree(c->claim_key); cudaFree(c->claimed); cudaFree(c->bucket_bits); cudaFree(c->vis_type); cudaFree(c->vis_list[0]); cudaFree(c->vis_list[1]); cudaFree(c->cache_pool); cudaFree(c->cache_tag);
+    cudaFree(c->claim_key); cudaFree(c->claimed); cudaFree(c->bucket_bits); cudaFree(c->vis_type); cudaFree(c->vis_list[0]); cudaFree(c->vis_list[1]); cudaFree(c->cache_pool); cudaFree(c->cache_tag); cudaFree(c->owned_list);
     cudaFree(c->minmax); cudaFree(c->raycast); cudaFree(c->dists_buf[0]); cudaFree(c->dists_buf[1]); cudaFree(c->depth_in); cudaFree(c->icp_partial);
     cudaFree(c->ds); cudaFree(c->l2_scratch); cudaFree(c->marks); cudaFree(c->shard_dev); cudaFree(c->sync_flags);
     for (int l = 0; l < MAX_LEVELS; ++l) {
@@ -218,7 +218,7 @@ int frame_end(tfb_ctx* c, int* ok) {
     }
     stamp(c, ST_FRAME);
     if ((r = fetch_state(c))) return r;  // the one wait of the frame
-    if (c->hs->shard_error) return set_err(c, TFB_ERR_STATE, "a cross-GPU barrier timed out: another rank stopped");
+    if (c->hs->shard_error) return set_err(c, TFB_ERR_STATE, c->hs->shard_error == 2 ? "the visibility-mark queue of the sharded raycast overflowed: marks were lost" : "a cross-GPU barrier timed out: another rank stopped");
     if (c->timing) {
         float t;
         for (int i = ST_PRE; i < ST_FRAME; ++i) {
@@ -498,6 +498,7 @@ int tfb_create(const tfb_params* p, void* stream, tfb_ctx** out) {
         const int cache_cap = p->num_blocks < (1 << 17) ? p->num_blocks : (1 << 17);
         ok(dmalloc(&c->cache_pool, (size_t)cache_cap * BLOCK3));
         ok(dmalloc(&c->cache_tag, (size_t)c->total_entries));
+        ok(dmalloc(&c->owned_list, (size_t)c->total_entries));
         if (e == cudaSuccess) cudaMemsetAsync(c->cache_tag, 0, (size_t)c->total_entries * sizeof(unsigned long long), c->stream);
         c->shard.cache_pool = c->cache_pool; c->shard.cache_tag = c->cache_tag; c->shard.cache_cap = cache_cap;
         c->shard.cache_epoch = c->gather_epoch = 1u;   // the zeroed tags carry epoch 0: no copy yet
@@ -882,7 +883,7 @@ int tfb_process_frame_sharded(tfb_ctx* c, const uint16_t* depth_dev_or_null, int
     const uint16_t* landing = c->depth_in + (size_t)(c->frame_seq & 1u) * c->p.cols * c->p.rows;
     int r = do_frame(c, landing, 0, ok, true);
     c->push_src = nullptr;
-    if (r == TFB_OK && c->hs->shard_error) return set_err(c, TFB_ERR_STATE, "a cross-GPU barrier timed out: another rank stopped");
+    if (r == TFB_OK && c->hs->shard_error) return set_err(c, TFB_ERR_STATE, c->hs->shard_error == 2 ? "the visibility-mark queue of the sharded raycast overflowed: marks were lost" : "a cross-GPU barrier timed out: another rank stopped");
     return r;
 }
 
@@ -1030,7 +1031,8 @@ static const char* const KNAMES[K_COUNT] = {
     "k_icp_begin", "k_icp_iteration[L0]", "k_icp_iteration[L1]", "k_icp_iteration[L2]", "k_icp_iteration[L3]", "(unused)",
     "k_pose_set", "k_set_type3", "k_mark", "k_alloc", "k_visible_list", "k_list_flip", "k_integrate_begin", "k_integrate",
     "k_minmax_init", "k_expected_depths", "k_raycast", "k_icp_maps", "k_reset_scene", "k_icp_all", "k_render_grey",
-    "k_raycast_sharded", "k_model_maps", "k_pyramid_maps", "k_shard_barrier", "k_push_frame", "k_wait_frame", "k_gather_foreign"};
+    "k_raycast_sharded", "k_model_maps", "k_pyramid_maps", "k_shard_barrier", "k_push_frame", "k_wait_frame", "k_gather_foreign",
+    "k_owned_list"};
 
 int tfb_ktiming_enable(tfb_ctx* c, int on) {
     if (!c) return TFB_ERR_ARG;
