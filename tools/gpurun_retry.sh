@@ -2,7 +2,7 @@
 # usage: tools/gpurun_retry.sh <timeout-seconds> <command string>   — retries while the pod answers "busy" (exit code 3)
 T=$1; shift
 for i in $(seq 1 40); do
-  /usr/local/graft/bin/gpurun --timeout "$T" -- "$@"
+  /usr/local/graft/bin/gpurun ${GPUS:+--gpus $GPUS} --timeout "$T" -- "$@"
   rc=$?
   if [ $rc -ne 3 ]; then exit $rc; fi
   sleep 90

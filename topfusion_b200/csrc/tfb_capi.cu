@@ -59,7 +59,7 @@ cudaError_t dmalloc(T** p, size_t n) { return cudaMalloc((void**)p, n * sizeof(T
 
 void free_all(tfb_ctx* c) {
     cudaFree(c->table); cudaFree(c->vba); cudaFree(c->vba_free); cudaFree(c->excess_free);
-    cudaFree(c->claim_key); cudaFree(c->claimed); cudaFree(c->bucket_bits); cudaFree(c->vis_type); cudaFree(c->vis_list[0]); cudaFree(c->vis_list[1]); cudaFree(c->cache_pool); cudaFree(c->cache_tag); cudaFree(c->owned_list);
+    cudaFree(c->claim_key); cudaFree(c->claimed); cudaFree(c->bucket_bits); cudaFree(c->vis_type); cudaFree(c->vis_list[0]); cudaFree(c->vis_list[1]); cudaFree(c->cache_pool); cudaFree(c->cache_tag);
     cudaFree(c->minmax); cudaFree(c->raycast); cudaFree(c->dists_buf[0]); cudaFree(c->dists_buf[1]); cudaFree(c->depth_in); cudaFree(c->icp_partial);
     cudaFree(c->ds); cudaFree(c->l2_scratch); cudaFree(c->marks); cudaFree(c->shard_dev); cudaFree(c->sync_flags);
     for (int l = 0; l < MAX_LEVELS; ++l) {
@@ -498,7 +498,6 @@ int tfb_create(const tfb_params* p, void* stream, tfb_ctx** out) {
         const int cache_cap = p->num_blocks < (1 << 17) ? p->num_blocks : (1 << 17);
         ok(dmalloc(&c->cache_pool, (size_t)cache_cap * BLOCK3));
         ok(dmalloc(&c->cache_tag, (size_t)c->total_entries));
-        ok(dmalloc(&c->owned_list, (size_t)c->total_entries));
         if (e == cudaSuccess) cudaMemsetAsync(c->cache_tag, 0, (size_t)c->total_entries * sizeof(unsigned long long), c->stream);
         c->shard.cache_pool = c->cache_pool; c->shard.cache_tag = c->cache_tag; c->shard.cache_cap = cache_cap;
         c->shard.cache_epoch = c->gather_epoch = 1u;   // the zeroed tags carry epoch 0: no copy yet
@@ -1031,8 +1030,7 @@ static const char* const KNAMES[K_COUNT] = {
     "k_icp_begin", "k_icp_iteration[L0]", "k_icp_iteration[L1]", "k_icp_iteration[L2]", "k_icp_iteration[L3]", "(unused)",
     "k_pose_set", "k_set_type3", "k_mark", "k_alloc", "k_visible_list", "k_list_flip", "k_integrate_begin", "k_integrate",
     "k_minmax_init", "k_expected_depths", "k_raycast", "k_icp_maps", "k_reset_scene", "k_icp_all", "k_render_grey",
-    "k_raycast_sharded", "k_model_maps", "k_pyramid_maps", "k_shard_barrier", "k_push_frame", "k_wait_frame", "k_gather_foreign",
-    "k_owned_list"};
+    "k_raycast_sharded", "k_model_maps", "k_pyramid_maps", "k_shard_barrier", "k_push_frame", "k_wait_frame", "k_gather_foreign"};
 
 int tfb_ktiming_enable(tfb_ctx* c, int on) {
     if (!c) return TFB_ERR_ARG;

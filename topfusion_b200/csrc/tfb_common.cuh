@@ -14,7 +14,7 @@ enum KernelId {
     K_BILATERAL = 0, K_DEPTH_PYR, K_POINTS_NORMALS, K_RESIZE_MAPS, K_COMPUTE_DISTS, K_TRUNCATE,
     K_ICP_BEGIN, K_ICP_L0, K_ICP_L1, K_ICP_L2, K_ICP_L3, K_POSE_UPDATE, K_POSE_SET,
     K_SET_TYPE3, K_MARK, K_ALLOC, K_VISIBLE_LIST, K_LIST_FLIP, K_INTEGRATE_BEGIN, K_INTEGRATE,
-    K_MINMAX_INIT, K_EXPECTED_DEPTHS, K_RAYCAST, K_ICP_MAPS, K_RESET_SCENE, K_ICP_ALL, K_RENDER_GREY, K_RAYCAST_SHARDED, K_MODEL_MAPS, K_PYR_MAPS, K_SHARD_BARRIER, K_PUSH_FRAME, K_WAIT_FRAME, K_GATHER_FOREIGN, K_OWNED_LIST, K_COUNT
+    K_MINMAX_INIT, K_EXPECTED_DEPTHS, K_RAYCAST, K_ICP_MAPS, K_RESET_SCENE, K_ICP_ALL, K_RENDER_GREY, K_RAYCAST_SHARDED, K_MODEL_MAPS, K_PYR_MAPS, K_SHARD_BARRIER, K_PUSH_FRAME, K_WAIT_FRAME, K_GATHER_FOREIGN, K_COUNT
 };
 constexpr int KT_MAX_EVENTS = 512;
 
@@ -74,8 +74,7 @@ struct DevState {
     int int_cursor;             // next visible-list position k_integrate hands out
     int shard_error;            // a cross-GPU barrier timed out
     int n_cached;               // sharded scene: foreign visible blocks copied into the local cache this frame
-    int n_owned;                // sharded scene: entries of the current visible list whose payload this rank holds (k_owned_list)
-    int pad2_[1];
+    int pad2_[2];
 };
 
 // payload owner of a block when the scene is sharded (new; the reference is single-GPU).  A different mix than
@@ -190,7 +189,6 @@ struct tfb_ctx {
     tfb::ShardView* shard_dev; // device copy (kernels that take it by pointer)
     unsigned int attached;     // bit r set once rank r's buffers are attached
     unsigned int* marks;       // incoming visibility marks: [0] count, [1] pad, then 2 words per mark
-    int* owned_list;                 // sharded scene: the entries of the visible list this rank integrates (k_owned_list)
     unsigned int* cache_pool;        // sharded scene: this frame's copies of the foreign visible blocks (2 KB each)
     unsigned long long* cache_tag;   // per hash slot: epoch << 32 | index into cache_pool
     unsigned int* sync_flags;  // TFB_MAX_SHARDS words: the barrier epochs the other ranks have published here
