@@ -95,3 +95,37 @@ def test_tracking_failure_is_reported(gpu, s0_frames):
         assert not ok
     finally:
         g.close()
+
+
+def test_persistent_icp_is_reproducible_over_many_launches(gpu, s0_frames):
+    """k_icp_all synchronises its 148 CTAs through epoch-stamped partial rows that every CTA polls (no counter, no fence):
+    each 64-bit word carries {sum, epoch} and is written / read by one single-copy-atomic access (the round-1 layout
+    relied on 32-byte sectors being written as a unit).  A reader that ever accepted a stale or torn word would fold a sum of
+    another iteration: the 19-iteration result would then differ between launches.  300 launches, bit for bit."""
+    depth, _, _ = s0_frames
+    g = gpu.Context()
+    try:
+        g.preprocess(depth[0])
+        for lvl in range(3):
+            g.set_level(3, lvl, g.level(1, lvl)); g.set_level(4, lvl, g.level(2, lvl))
+        g.preprocess(depth[6])
+        ok0, a0 = g.estimate_transform()
+        assert ok0
+        for _ in range(300):
+            ok, a = g.estimate_transform()
+            assert ok and np.array_equal(a.view(np.uint32), a0.view(np.uint32))
+    finally:
+        g.close()
+
+
+def test_icp_parameter_ranges_are_validated(gpu):
+    """fixed-width encodings: 64 row epochs per launch -> at most 63 iterations per coarse-to-fine loop; 6 bits of
+    step in the allocation claim key -> mu / voxel_size is bounded"""
+    with pytest.raises(gpu.TfbError):
+        gpu.Context(icp_iters=(40, 20, 10, 0))
+    with pytest.raises(gpu.TfbError):
+        gpu.Context(icp_iters=(10, -1, 4, 0))
+    with pytest.raises(gpu.TfbError):
+        gpu.Context(mu=0.5, voxel_size=0.002)
+    c = gpu.Context(icp_iters=(30, 20, 13, 0))     # 63 in total: accepted
+    c.close()

@@ -532,7 +532,8 @@ int tfb_create(const tfb_params* p, void* stream, tfb_ctx** out) {
         }
     }
     c->icp_max_blocks = div_up(p->cols, 32) * div_up(p->rows, 8);
-    const size_t n_partial = (size_t)64 * (c->icp_max_blocks > 1024 ? c->icp_max_blocks : 1024) + 64;
+    // k_icp_all: 2 parities x one row of 32 x {fp32 sum, u32 epoch} per CTA = 128 floats per CTA
+    const size_t n_partial = (size_t)128 * (c->icp_max_blocks > 1024 ? c->icp_max_blocks : 1024) + 128;
     ok(dmalloc(&c->icp_partial, n_partial));
     if (e == cudaSuccess) cudaMemsetAsync(c->icp_partial, 0, n_partial * sizeof(float), c->stream);   // no stale epochs
     ok(cudaMalloc((void**)&c->ds, sizeof(DevState) + 64 * sizeof(float)));

@@ -456,13 +456,19 @@ struct IcpAllArgs {
 constexpr int ICPA_THREADS = 512, ICPA_WARPS = ICPA_THREADS / 32, ICPA_UNROLL = 5;   // one CTA per SM
 constexpr int ICP_LIST_SLOTS = 16;   // pixel slots per thread the valid-pixel list covers (16 x 75 776 = 1.2 M pixels; 32 KB of smem)
 
-// L2-scope load of a word of a partial row (rows are polled: they must never be served from a stale L1 line).  No acquire
-// fence is issued anywhere in the iteration loop: on sm_100a an acquire is MEMBAR + CCTL.IVALL, which throws away the SM's
-// L1 — and with it the vertex / normal maps this CTA re-reads in every one of the 10/5/4 iterations of a level.
-__device__ __forceinline__ float ld_partial(const float* p) {
-    float v;
-    asm volatile("ld.relaxed.gpu.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+// A word of a partial row is 64 bits: the fp32 partial sum in the low half, the epoch of the iteration that produced it in the
+// high half, written with ONE st.relaxed.gpu.b64 and read with ONE ld.relaxed.gpu.b64.  An aligned 64-bit scalar access is
+// single-copy atomic in the PTX memory model, so a reader that sees the epoch in a word holds that epoch's sum — per word,
+// with no assumption about sectors, warps or store coalescing, and with no fence: on sm_100a an acquire is MEMBAR + CCTL.IVALL,
+// which throws away the SM's L1 — and with it the vertex / normal maps this CTA re-reads in every one of the 10/5/4 iterations
+// of a level.  (Round 1 packed seven sums and one epoch per 32-byte sector and relied on the sector being written as a unit.)
+__device__ __forceinline__ unsigned long long ld_partial(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
+}
+__device__ __forceinline__ void st_partial(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 #ifdef TFB_ICP_PROFILE
@@ -638,23 +644,19 @@ __global__ void __launch_bounds__(ICPA_THREADS, 1)
                 if (lane < ICP_ACC) s_warp[warp][lane] = v[0];
             }
             __syncthreads();
-            // The CTA's row of partials IS its barrier arrival: 128 bytes = four 32-byte sectors, each holding seven sums and,
-            // in its eighth word, the epoch of this iteration (unique across iterations and launches).  A sector is written
-            // and read as a unit, so a reader that sees the epoch in a sector sees that sector's sums — no fence, no counter,
-            // no second round trip: the fold below simply re-reads a row until its four epochs match.  Rows are double
-            // buffered by iteration parity; a CTA can only write iteration i+2 after every CTA has finished reading i.
+            // The CTA's row of partials IS its barrier arrival: 32 words of 64 bits, {sum, epoch} each (28 sums + 4 words of
+            // padding so every lane of the fold runs the same code); the epoch is unique across iterations and launches.  No
+            // counter, no fence, no second round trip: the fold below re-reads a word until it carries the epoch.  Rows are
+            // double buffered by iteration parity; a CTA can only write iteration i+2 after every CTA has finished reading i.
             const unsigned int epoch = a.epoch_base + (unsigned)iter_global + 1u;
-            float* prow = partial + (size_t)(iter_global & 1) * nblk * 32;
+            unsigned long long* prow = reinterpret_cast<unsigned long long*>(partial) + (size_t)(iter_global & 1) * nblk * 32;
             if (tid < 32) {
-                float val = __uint_as_float(epoch);
-                if ((tid & 7) != 7) {
-                    const int term = (tid >> 3) * 7 + (tid & 7);
-                    float sacc = 0.f;
+                float sacc = 0.f;
+                if (tid < ICP_ACC) {
 #pragma unroll
-                    for (int wi = 0; wi < ICPA_WARPS; ++wi) sacc += s_warp[wi][term];
-                    val = sacc;
+                    for (int wi = 0; wi < ICPA_WARPS; ++wi) sacc += s_warp[wi][tid];
                 }
-                asm volatile("st.relaxed.gpu.global.f32 [%0], %1;" ::"l"(prow + blockIdx.x * 32 + tid), "f"(val) : "memory");
+                st_partial(prow + blockIdx.x * 32 + tid, ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(sacc));
             }
             ICP_STAMP(2);
             ICP_STAMP(3);
@@ -663,16 +665,15 @@ __global__ void __launch_bounds__(ICPA_THREADS, 1)
             {
                 // warp p takes CTAs p, p+16, ...; lane = word of the row; all of a warp's loads are in flight before the first add
                 const int k = lane, part = warp;
-                const bool flag_lane = (k & 7) == 7;
                 double sd = 0;
                 for (int b0 = part; b0 < nblk; b0 += ICPA_WARPS * 10) {
-                    float tmp[10];
-                    // poll: every round re-reads ALL rows that are still missing at once (one L2 round trip per round, not one
-                    // per late row), until the last of this warp's rows carries the epoch
+                    unsigned long long tmp[10];
+                    // poll: every round re-reads ALL words that are still missing at once (one L2 round trip per round, not one
+                    // per late row), until the last of this warp's rows carries the epoch in every word
                     unsigned int pending = 0;
 #pragma unroll
                     for (int j = 0; j < 10; ++j) {
-                        tmp[j] = __uint_as_float(epoch);
+                        tmp[j] = (unsigned long long)epoch << 32;
                         if (b0 + j * ICPA_WARPS < nblk) pending |= 1u << j;
                     }
                     while (pending) {
@@ -682,20 +683,19 @@ __global__ void __launch_bounds__(ICPA_THREADS, 1)
                         unsigned int still = 0;
 #pragma unroll
                         for (int j = 0; j < 10; ++j)
-                            if ((pending & (1u << j)) && __any_sync(0xffffffffu, flag_lane && __float_as_uint(tmp[j]) != epoch)) still |= 1u << j;
+                            if ((pending & (1u << j)) && __any_sync(0xffffffffu, (unsigned int)(tmp[j] >> 32) != epoch)) still |= 1u << j;
                         pending = still;
                     }
 #pragma unroll
-                    for (int j = 0; j < 10; ++j) sd += (double)tmp[j];
+                    for (int j = 0; j < 10; ++j) sd += (double)__uint_as_float((unsigned int)tmp[j]);
                 }
-                s_part[part][k] = sd;   // the flag lanes sum nonsense; nobody reads them
+                s_part[part][k] = sd;   // lanes 28..31 sum the padding words (zeros); nobody reads them
             }
             __syncthreads();
             if (tid < ICP_ACC) {
-                const int word = (tid / 7) * 8 + (tid % 7);
                 double sd = 0;
 #pragma unroll
-                for (int p = 0; p < ICPA_WARPS; ++p) sd += s_part[p][word];
+                for (int p = 0; p < ICPA_WARPS; ++p) sd += s_part[p][tid];
                 s_tot[tid] = sd;
             }
             __syncthreads();
