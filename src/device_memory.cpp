@@ -2,6 +2,7 @@
 // share, the last owner frees, user-provided memory is never freed).
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 #include <utility>
 #include <tfusion/cuda/device_memory.hpp>
 #include "detail.hpp"
@@ -16,14 +17,17 @@ void cuda::error(const char* error_string, const char* file, const int line, con
 
 namespace detail {
 tfb_ctx* util_ctx() {
+    // created once, by whichever thread gets here first; lives as long as the process (it owns the stream that stand-alone
+    // DeviceMemory / imgproc / ProjectiveICP calls run on, and static destructors may still use it)
     static tfb_ctx* c = nullptr;
-    if (!c) {
+    static std::once_flag once;
+    std::call_once(once, [] {
         tfb_params p;
         tfb_default_params(&p);
         p.cols = 8; p.rows = 8; p.num_blocks = 1; p.num_buckets = 2; p.excess_size = 1;
         int rc = tfb_create(&p, nullptr, &c);
         if (rc != TFB_OK) cuda::error("cannot create a CUDA context (no device? there is no CPU fallback)", __FILE__, __LINE__);
-    }
+    });
     return c;
 }
 void check(int rc, const char* what, const char* file, int line) {
@@ -38,11 +42,11 @@ DeviceMemory::DeviceMemory(void* ptr_arg, size_t sizeBytes_arg) : data_(ptr_arg)
 DeviceMemory::DeviceMemory(size_t sizeBytes_arg) : data_(0), sizeBytes_(0), refcount_(0) { create(sizeBytes_arg); }
 DeviceMemory::~DeviceMemory() { release(); }
 DeviceMemory::DeviceMemory(const DeviceMemory& o) : data_(o.data_), sizeBytes_(o.sizeBytes_), refcount_(o.refcount_) {
-    if (refcount_) ++*refcount_;
+    if (refcount_) __atomic_add_fetch(refcount_, 1, __ATOMIC_RELAXED);
 }
 DeviceMemory& DeviceMemory::operator=(const DeviceMemory& o) {
     if (this != &o) {
-        if (o.refcount_) ++*o.refcount_;
+        if (o.refcount_) __atomic_add_fetch(o.refcount_, 1, __ATOMIC_RELAXED);
         release();
         data_ = o.data_; sizeBytes_ = o.sizeBytes_; refcount_ = o.refcount_;
     }
@@ -58,7 +62,7 @@ void DeviceMemory::create(size_t sizeBytes_arg) {
     }
 }
 void DeviceMemory::release() {
-    if (refcount_ && --*refcount_ == 0) {
+    if (refcount_ && __atomic_sub_fetch(refcount_, 1, __ATOMIC_ACQ_REL) == 0) {
         delete refcount_;
         tfb_dev_free(data_);
     }
@@ -89,11 +93,11 @@ DeviceMemory2D::DeviceMemory2D(int rows_arg, int colsBytes_arg, void* data_arg, 
 DeviceMemory2D::~DeviceMemory2D() { release(); }
 DeviceMemory2D::DeviceMemory2D(const DeviceMemory2D& o)
     : data_(o.data_), step_(o.step_), colsBytes_(o.colsBytes_), rows_(o.rows_), refcount_(o.refcount_) {
-    if (refcount_) ++*refcount_;
+    if (refcount_) __atomic_add_fetch(refcount_, 1, __ATOMIC_RELAXED);
 }
 DeviceMemory2D& DeviceMemory2D::operator=(const DeviceMemory2D& o) {
     if (this != &o) {
-        if (o.refcount_) ++*o.refcount_;
+        if (o.refcount_) __atomic_add_fetch(o.refcount_, 1, __ATOMIC_RELAXED);
         release();
         data_ = o.data_; step_ = o.step_; colsBytes_ = o.colsBytes_; rows_ = o.rows_; refcount_ = o.refcount_;
     }
@@ -110,7 +114,7 @@ void DeviceMemory2D::create(int rows_arg, int colsBytes_arg) {
     }
 }
 void DeviceMemory2D::release() {
-    if (refcount_ && --*refcount_ == 0) {
+    if (refcount_ && __atomic_sub_fetch(refcount_, 1, __ATOMIC_ACQ_REL) == 0) {
         delete refcount_;
         tfb_dev_free(data_);
     }

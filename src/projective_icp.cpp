@@ -53,9 +53,10 @@ bool ProjectiveICP::estimateTransform(Affine3f& affine, const Intr& intr, const 
     int ok = 0;
     TF_CHECK(tfb_icp_estimate_ext(detail::util_ctx(), levels, vc, nc, vp, np, vprev[0].cols(), vprev[0].rows(), &iters_[0], dist_thres_,
                                   angle_thres_, k, aff, &ok));
-    if (ok)
-        for (int r = 0; r < 4; ++r)
-            for (int c = 0; c < 4; ++c) affine.matrix(r, c) = aff[r * 4 + c];
+    // like the reference (projective_icp.cpp:174,197-209), `affine` holds the product of the iterations that succeeded —
+    // the whole estimate when ok, Identity or a partial product when tracking failed
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) affine.matrix(r, c) = aff[r * 4 + c];
     return ok != 0;
 }
 

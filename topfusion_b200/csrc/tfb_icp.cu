@@ -722,10 +722,14 @@ __global__ void __launch_bounds__(ICPA_THREADS, 1)
     if (tid == 0) {
         ds->icp_failed = ok ? 0 : 1;
         ds->icp_corresp = (int)s_tot[ICP_TERMS];
+        // ds->affine: the running product — on failure the product of the iterations before the failing one, which is what
+        // ProjectiveICP::estimateTransform leaves in its `affine` argument when it returns false (projective_icp.cpp:197-203)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) ds->affine[i] = s_aff[i];
         if (ok) {
             float aff[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) { aff[i] = s_aff[i]; ds->affine[i] = aff[i]; }
+            for (int i = 0; i < 16; ++i) aff[i] = s_aff[i];
             if (a.update_pose) {
                 float prev[16], nw[16];
 #pragma unroll
@@ -813,7 +817,10 @@ static int launch_icp_args(tfb_ctx* c, IcpAllArgs& a, int total) {
         TFB_CUDA(c, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
         if (per_sm < 1) return set_err(c, TFB_ERR_CUDA, "icp: kernel does not fit on an SM");
         c->icp_grid = sms;   // one CTA per SM: the partial rows every CTA folds grow with the grid
-        if (c->icp_grid > c->icp_max_blocks) c->icp_grid = c->icp_max_blocks;
+        // the partial buffer holds max(icp_max_blocks, 1024) rows whatever the context's own image size is: a small context
+        // (the C++ mirror's utility context is 8x8) must not squeeze tfb_icp_estimate_ext's 640x480 pyramids into one CTA
+        const int cap = c->icp_max_blocks > 1024 ? c->icp_max_blocks : 1024;
+        if (c->icp_grid > cap) c->icp_grid = cap;
     }
     a.epoch_base = (unsigned int)(++c->icp_launches) * 64u;   // rows of earlier launches can never match
     DevState* ds = c->ds;
