@@ -101,6 +101,8 @@ public:
     long long voxelUpdatesLastFrame() const;
     // the reconstruction as surface points (what apps/demo.cpp's take_cloud stub would fetch): x, y, z, 1 per point, world metres
     void extractPoints(cuda::DeviceArray<float>& points4, int& count);
+    // the cloud of the current view (renderPointCloud_device, cuda/VisualisationHelper.hpp:150-198 of the reference)
+    void renderPointCloud(cuda::DeviceArray<float>& points4, int& count, bool skipPoints = false);
     void saveScene(const std::string& path);
     void loadScene(const std::string& path);
 

@@ -235,6 +235,11 @@ TFB_API void* tfb_stream(tfb_ctx* c);   /* the cudaStream_t the context runs on 
  * (take_cloud, apps/demo.cpp:70-77) and a dormant per-pixel renderPointCloud_device (VisualisationHelper.hpp:150-198).
  * *n_out = points found; min(*n_out, capacity) were written (call with capacity 0 to size the buffer).  Order is arbitrary. */
 TFB_API int tfb_extract_points(tfb_ctx* c, float* points_dev, int capacity, int* n_out);
+/* renderPointCloud_device, include/tfusion/cuda/VisualisationHelper.hpp:150-198 (dormant in the reference: its caller
+ * take_cloud is a stub, apps/demo.cpp:70-77): the surface points one view sees — raycast from pose_c2w (NULL: the current
+ * pose) without touching visibility, every hit with a light-facing SDF-gradient normal, x y z 1 in world metres.
+ * skip_points != 0 keeps pixels with odd x and odd y only.  n_out = points found; min(n_out, capacity) are written. */
+TFB_API int tfb_render_point_cloud(tfb_ctx* c, const float* pose_c2w_or_null, int skip_points, float* points_dev, int capacity, int* n_out);
 /* allocated blocks + pose history in one file; tfb_scene_load restores them into a context created with the same voxel
  * size, band and hash geometry, rebuilds the visible list and the model maps for the last pose, and tracking goes on. */
 TFB_API int tfb_scene_save(tfb_ctx* c, const char* path);

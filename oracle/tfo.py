@@ -230,6 +230,13 @@ class Oracle:
         self.L.lib.tfo_render_image(self.h, _p(_f32(pose).reshape(16)), _p(out))
         return out
 
+    def render_point_cloud(self, pose_c2w=None, skip_points=False):
+        pose = self.pose() if pose_c2w is None else pose_c2w
+        out = np.empty((self.rows * self.cols, 4), np.float32)
+        self.L.lib.tfo_render_point_cloud.restype = C.c_int
+        n = self.L.lib.tfo_render_point_cloud(self.h, _p(_f32(pose).reshape(16)), C.c_int(1 if skip_points else 0), _p(out))
+        return out[:n].copy()
+
     def process_frame(self, depth) -> bool:
         d = np.ascontiguousarray(depth, dtype=np.uint16)
         assert d.shape == (self.rows, self.cols)

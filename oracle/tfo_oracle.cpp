@@ -665,6 +665,31 @@ struct Oracle {
             }
     }
 
+    // renderPointCloud_device (include/tfusion/cuda/VisualisationHelper.hpp:150-198; dormant in the reference, its caller
+    // take_cloud is a stub): per pixel of a raycast that leaves visibility alone — foundPoint = w > 0 (:164-166);
+    // computeNormalAndAngle clears it when the SDF-gradient normal faces away from the light (:168, the same call
+    // processPixelGrey makes: a shaded value of 0 <=> foundPoint false, drawPixelGrey writes >= 51 otherwise); skipPoints keeps
+    // pixels with odd x and odd y (:170); locations = point * voxelSize, w = 1 (:189-192).  Raster order here; the reference's
+    // order is the arrival order of its CTAs.  Returns the number of points.
+    int render_point_cloud(const Pose& pose_c2w, bool skip_points, float* out_xyzw) {
+        raycast_pass(pose_c2w, false);
+        float light[3] = {-pose_c2w.m[2], -pose_c2w.m[6], -pose_c2w.m[10]};
+        int n = 0;
+        for (int y = 0; y < p.rows; ++y)
+            for (int x = 0; x < p.cols; ++x) {
+                size_t id = (size_t)x + (size_t)y * p.cols;
+                uint8_t px[4];
+                k::shade_pixel_grey(px, &raycast[4 * id], vba.data(), table.data(), light, g);
+                bool found = px[0] != 0;
+                if (skip_points && ((x % 2 == 0) || (y % 2 == 0))) found = false;
+                if (!found) continue;
+                for (int c = 0; c < 3; ++c) out_xyzw[4 * n + c] = raycast[4 * id + c] * p.voxel_size;
+                out_xyzw[4 * n + 3] = 1.0f;
+                ++n;
+            }
+        return n;
+    }
+
     // ProjectiveICP::estimateTransform (points variant), projective_icp.cpp:169-212
     bool estimate_transform(Pose& affine) {
         IcpSetup s;
@@ -792,6 +817,7 @@ void tfo_allocate(void* h, const float* pose_w2c, const float* dists) { Pose p; 
 void tfo_integrate(void* h, const float* pose_w2c, const float* dists) { Pose p; memcpy(p.m, pose_w2c, 64); ((Oracle*)h)->integrate(p, dists); }
 void tfo_expected_depths(void* h, const float* pose_w2c) { Pose p; memcpy(p.m, pose_w2c, 64); ((Oracle*)h)->expected_depths(p); }
 void tfo_icp_maps(void* h, const float* pose_c2w, float* points, float* normals) { Pose p; memcpy(p.m, pose_c2w, 64); ((Oracle*)h)->icp_maps(p, points, normals); }
+int tfo_render_point_cloud(void* h, const float* pose_c2w, int skip_points, float* out_xyzw) { Pose p; memcpy(p.m, pose_c2w, 64); return ((Oracle*)h)->render_point_cloud(p, skip_points != 0, out_xyzw); }
 void tfo_render_image(void* h, const float* pose_c2w, uint8_t* out_rgba) { Pose p; memcpy(p.m, pose_c2w, 64); ((Oracle*)h)->render_image(p, out_rgba); }
 void tfo_raycast(void* h, const float* pose_c2w, int update_visible) { Pose p; memcpy(p.m, pose_c2w, 64); ((Oracle*)h)->raycast_pass(p, update_visible != 0); }
 

@@ -113,6 +113,11 @@ void TopFu::extractPoints(cuda::DeviceArray<float>& points4, int& count) {
     TF_CHECK(tfb_extract_points(ctx_, points4.ptr(), n, &count));
 }
 
+void TopFu::renderPointCloud(cuda::DeviceArray<float>& points4, int& count, bool skipPoints) {
+    points4.create((size_t)params_.rows * params_.cols * 4);
+    TF_CHECK(tfb_render_point_cloud(ctx_, 0, skipPoints ? 1 : 0, points4.ptr(), params_.rows * params_.cols, &count));
+}
+
 void TopFu::saveScene(const std::string& path) { TF_CHECK(tfb_scene_save(ctx_, path.c_str())); }
 
 void TopFu::loadScene(const std::string& path) {

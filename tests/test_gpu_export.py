@@ -91,3 +91,36 @@ def test_scene_save_load_and_resume_tracking(gpu, s1_frames, tmp_path):
             gpu.Context(voxel_size=0.004).load_scene(path)     # written with another voxel size
     finally:
         a.close(); b.close()
+
+
+def test_view_point_cloud_matches_the_reference_function(gpu, s1_frames):
+    """tfb_render_point_cloud against the oracle's render_point_cloud, which follows the reference's own (dormant)
+    renderPointCloud_device (include/tfusion/cuda/VisualisationHelper.hpp:150-198) with the reference's castRay and
+    computeNormalAndAngle underneath (oracle/_ref build; bit-identical port otherwise).  Same scene on both sides (injected
+    ground-truth poses, IEEE integration arithmetic = the oracle's), same view, with and without skipPoints: the clouds must be
+    the same SET of points, bit for bit — the order is unspecified on both sides (CTA arrival order in the reference)."""
+    from oracle import tfo
+    depth, poses, _ = s1_frames
+    L = tfo.Lib("ref" if tfo.have_ref() else "port")
+    o = tfo.Oracle(lib=L)
+    g = gpu.Context(ieee_arith=1)
+    try:
+        for i in range(3):
+            dists = L.compute_dists(depth[i])
+            w2c = L.pose_inv(poses[i].astype(np.float32))
+            o.allocate(w2c, dists); g.allocate(w2c, dists)
+            o.integrate(w2c, dists); g.integrate(w2c, dists)
+            o.expected_depths(w2c); g.expected_depths(w2c)
+        view = poses[2].astype(np.float32)
+        for skip in (False, True):
+            po = o.render_point_cloud(view, skip)
+            pg = g.render_point_cloud(view, skip)
+            assert po.shape[0] > (10000 if skip else 40000)
+            assert pg.shape == po.shape
+            assert np.all(pg[:, 3] == 1.0)
+            assert np.array_equal(_sorted_rows(pg), _sorted_rows(po))
+        # the view sees the sphere of radius 0.35 m at (0, 0, 1.2)
+        d = np.linalg.norm(pg[:, :3] - np.array([0, 0, 1.2], np.float32), axis=1)
+        assert (np.abs(d - 0.35) < 0.004).sum() > 2000
+    finally:
+        g.close(); o.close()

@@ -98,6 +98,7 @@ def lib() -> C.CDLL:
             "tfb_frame_begin": [C.c_void_p, C.c_void_p],
             "tfb_frame_raycast": [C.c_void_p],
             "tfb_extract_points": [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)],
+            "tfb_render_point_cloud": [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)],
             "tfb_scene_save": [C.c_void_p, C.c_char_p],
             "tfb_scene_load": [C.c_void_p, C.c_char_p],
             "tfb_shard_push_frame": [C.c_void_p, C.c_void_p],
@@ -338,6 +339,17 @@ class Context:
         self._ck(self.L.tfb_extract_points(self.h, buf.ptr, C.c_int(n.value), C.byref(m)))
         assert m.value == n.value
         out = self.download(buf, (n.value, 4), np.float32)
+        buf.free()
+        return out
+
+    def render_point_cloud(self, pose_c2w=None, skip_points=False) -> np.ndarray:
+        """the reference's renderPointCloud_device: surface points of one view, float32 [n, 4] in world metres, arbitrary order"""
+        cap = self.rows * self.cols
+        buf = DevBuf(cap * 16)
+        n = C.c_int(0)
+        p = _np_ptr(_f32(pose_c2w).reshape(16)) if pose_c2w is not None else None
+        self._ck(self.L.tfb_render_point_cloud(self.h, p, C.c_int(1 if skip_points else 0), buf.ptr, C.c_int(cap), C.byref(n)))
+        out = self.download(buf, (n.value, 4), np.float32) if n.value else np.zeros((0, 4), np.float32)
         buf.free()
         return out
 

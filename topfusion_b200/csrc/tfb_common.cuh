@@ -275,6 +275,7 @@ int launch_rebuild_visible(tfb_ctx* c);
 int launch_expected_depths(tfb_ctx* c, bool reset_image = false);
 int launch_icp_maps(tfb_ctx* c, float4* points, float4* normals, bool do_raycast = true);
 int launch_render_grey(tfb_ctx* c, uchar4* out);
+int launch_point_cloud(tfb_ctx* c, float4* out, int capacity, unsigned int* counter, bool skip_points);
 int launch_raycast(tfb_ctx* c, bool update_visible);
 // publish_epoch != 0: the last CTA to finish publishes that barrier epoch to every rank (this rank's rows and marks are out)
 int launch_raycast_sharded(tfb_ctx* c, bool viewer, unsigned int publish_epoch = 0u);

@@ -140,6 +140,26 @@ int tfb_extract_points(tfb_ctx* c, float* points_dev, int capacity, int* n_out) 
     return TFB_OK;
 }
 
+// renderPointCloud_device (include/tfusion/cuda/VisualisationHelper.hpp:150-198): the cloud of ONE view — a raycast from pose_c2w
+// (poses_.back() when null) that does not touch visibility, then every hit pixel with a light-facing SDF-gradient normal, in
+// world metres.  skip_points keeps only pixels with odd x and odd y, as the reference's flag does.  Order is unspecified.
+int tfb_render_point_cloud(tfb_ctx* c, const float* pose_c2w_or_null, int skip_points, float* points_dev, int capacity, int* n_out) {
+    if (!c || !n_out || capacity < 0 || (capacity > 0 && !points_dev)) return TFB_ERR_ARG;
+    if (c->p.shard_count > 1) return set_err(c, TFB_ERR_STATE, "tfb_render_point_cloud: the mark queue doubles as the counter; use an unsharded context");
+    int r = tfb_sync(c);   // finishes a deferred tail
+    if (r) return r;
+    if (pose_c2w_or_null && (r = launch_pose_set(c, pose_c2w_or_null, false))) return r;
+    unsigned int* counter = c->marks;   // idle outside a sharded frame
+    TFB_CUDA(c, cudaMemsetAsync(counter, 0, sizeof(unsigned int), c->stream));
+    if ((r = launch_point_cloud(c, reinterpret_cast<float4*>(points_dev), capacity, counter, skip_points != 0))) return r;
+    unsigned int n = 0;
+    TFB_CUDA(c, cudaMemcpyAsync(&n, counter, sizeof(n), cudaMemcpyDeviceToHost, c->stream));
+    TFB_CUDA(c, cudaStreamSynchronize(c->stream));
+    TFB_CUDA(c, cudaMemsetAsync(counter, 0, sizeof(unsigned int), c->stream));
+    *n_out = (int)n;   // points found; only min(n, capacity) were written
+    return TFB_OK;
+}
+
 // ---- scene file ------------------------------------------------------------------------------------------
 // header: magic, version, voxel_size, mu, num_buckets, excess_size, n_blocks, n_poses; then n_poses x 16 floats;
 // then n_blocks x { short pos[3], pad; 512 x u32 voxels }.  The hash geometry of the loading context must match.
