@@ -56,23 +56,52 @@ def test_reference_mode_hover_sequence(gpu):
         g.close(); o.close()
 
 
-def test_reference_mode_state_after_five_frames(gpu, s0_frames):
-    """block set and TSDF after 5 reference-mode frames (before the drift explodes)"""
-    depth, _, _ = s0_frames
-    o, g, rows, tfo = _run(gpu, depth, 5)
-    try:
-        so, sg = tfo.allocated_set(o.table()), tfo.allocated_set(g.table())
-        assert len(so ^ sg) <= max(8, len(so) // 200), len(so ^ sg)
-        # TSDF within 1e-3 of truncation on the shared blocks (sdf is stored as value/32767 -> 33 counts)
-        bo, bg = o.blocks_by_pos(), g.blocks_by_pos()
-        shared = sorted(set(bo) & set(bg))[::5]
-        bad = tot = 0
-        for k in shared:
-            d = np.abs(bo[k]["sdf"].astype(np.int32) - bg[k]["sdf"].astype(np.int32))
-            bad += int((d > 33).sum()); tot += 512
-        assert bad / tot < 2e-3, (bad, tot)
-    finally:
-        g.close(); o.close()
+def _state_report(o, g, tfo):
+    """block-set symmetric difference and the histogram of |sdf difference| (LSB of 32767; 1e-3 of truncation = 32.8 LSB) on the
+    blocks both sides hold"""
+    so, sg = tfo.allocated_set(o.table()), tfo.allocated_set(g.table())
+    bo, bg = o.blocks_by_pos(), g.blocks_by_pos()
+    edges = [0, 1, 2, 4, 8, 16, 33, 1 << 17]
+    hist = np.zeros(len(edges) - 1, np.int64)
+    w_diff = 0
+    for k in set(bo) & set(bg):
+        d = np.abs(bo[k]["sdf"].astype(np.int32) - bg[k]["sdf"].astype(np.int32))
+        hist += np.histogram(d, bins=edges)[0]
+        w_diff += int((bo[k]["w"] != bg[k]["w"]).sum())
+    return {"blocks_oracle": len(so), "blocks_gpu": len(sg), "symdiff": len(so ^ sg), "voxels": int(hist.sum()), "weights_differing": w_diff,
+            "sdf_lsb_hist": {f"[{edges[i]},{edges[i + 1]})": int(hist[i]) for i in range(len(hist))}}
+
+
+def test_tracked_frames_state_report(gpu, s0_frames, s1_frames):
+    """Tracked frames (the pose comes from ICP, so it differs from the oracle's in its last bits — ICP sums are accumulated in
+    another order): per frame, the allocated-block symmetric difference and the TSDF difference histogram, in both modes.
+    Written to gpurun_out/tracked_state_report.json.  Bars: the north star's — block sets identical up to knife-edge blocks (a block
+    whose sample lies within a pose-bit of a block face), TSDF within 1e-3 of truncation on >= 99.8 % of the voxels."""
+    import json, os
+    from oracle import tfo
+    report = {}
+    for name, frames, n, kw in (("reference_mode_S0", s0_frames[0], 5, {}), ("corrected_mode_S1", s1_frames[0], 8, {"corrected_mode": 1})):
+        o = tfo.Oracle(**kw)
+        g = gpu.Context(ieee_arith=1, **kw)
+        try:
+            per_frame = []
+            for i in range(n):
+                assert o.process_frame(frames[i]) == g.process_frame(frames[i])
+                so, sg = tfo.allocated_set(o.table()), tfo.allocated_set(g.table())
+                per_frame.append({"frame": i, "blocks": len(so), "symdiff": len(so ^ sg),
+                                  "dt_m": float(np.abs(o.pose()[:3, 3] - g.pose()[:3, 3]).max())})
+                assert len(so ^ sg) <= max(8, len(so) // 200), (name, i, len(so ^ sg))
+            rep = _state_report(o, g, tfo)
+            rep["per_frame"] = per_frame
+            report[name] = rep
+            over = rep["sdf_lsb_hist"]["[33,131072)"]
+            assert over <= 2e-3 * rep["voxels"], (name, rep)
+        finally:
+            g.close(); o.close()
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "tracked_state_report.json"), "w") as f:
+        json.dump(report, f, indent=1)
 
 
 def test_frame0_is_bit_exact(gpu, s1_frames):
