@@ -59,7 +59,7 @@ cudaError_t dmalloc(T** p, size_t n) { return cudaMalloc((void**)p, n * sizeof(T
 
 void free_all(tfb_ctx* c) {
     cudaFree(c->table); cudaFree(c->vba); cudaFree(c->vba_free); cudaFree(c->excess_free);
-    cudaFree(c->claim_key); cudaFree(c->claimed); cudaFree(c->bucket_bits); cudaFree(c->vis_type); cudaFree(c->vis_list[0]); cudaFree(c->vis_list[1]); cudaFree(c->cache_pool); cudaFree(c->cache_tag);
+    cudaFree(c->claim_key); cudaFree(c->claimed); cudaFree(c->bucket_bits); cudaFree(c->block_dir); cudaFree(c->vis_type); cudaFree(c->vis_list[0]); cudaFree(c->vis_list[1]); cudaFree(c->cache_pool); cudaFree(c->cache_tag);
     cudaFree(c->minmax); cudaFree(c->raycast); cudaFree(c->dists_buf[0]); cudaFree(c->dists_buf[1]); cudaFree(c->depth_in); cudaFree(c->icp_partial);
     cudaFree(c->ds); cudaFree(c->l2_scratch); cudaFree(c->marks); cudaFree(c->shard_dev); cudaFree(c->sync_flags);
     for (int l = 0; l < MAX_LEVELS; ++l) {
@@ -490,6 +490,7 @@ int tfb_create(const tfb_params* p, void* stream, tfb_ctx** out) {
     ok(dmalloc(&c->claim_key, (size_t)c->total_entries));
     ok(dmalloc(&c->claimed, (size_t)c->total_entries));
     ok(dmalloc(&c->bucket_bits, (size_t)(p->num_buckets + 31) / 32));
+    ok(dmalloc(&c->block_dir, DIR_CELLS));
     ok(dmalloc(&c->vis_type, (size_t)c->total_entries));
     ok(dmalloc(&c->vis_list[0], (size_t)c->total_entries));
     ok(dmalloc(&c->vis_list[1], (size_t)c->total_entries));

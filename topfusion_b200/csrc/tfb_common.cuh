@@ -36,6 +36,23 @@ struct __align__(16) HashEntry {
 };
 static_assert(sizeof(HashEntry) == 16, "HashEntry");
 
+// Block directory (new; the reference resolves every block through the hash): a dense window of DIR_N^3 blocks centred on the
+// world origin — the first camera pose — with one 8-byte cell {slot of the hash entry, ptr into the voxel pool} per block, {-1,-1}
+// where no block is allocated.  It is an INDEX of the hash table, written where entries are written (allocation, scene load) and
+// cleared with it (reset); the table stays the authority and serves blocks outside the window.  What it buys the raycast: a block
+// lookup is ONE load instead of occupancy word -> entry -> chain, and the loads are spatially coherent — a ray's next block and
+// the up to eight blocks of a trilinear read sit in the same or a neighbouring 128-byte line (cells are tiled 4x2x2 per line),
+// where hashing scatters them over a 19 MB table on purpose.  256^3 cells = 128 MiB of the 180 GB: 10 m at 5 mm voxels, 4 m at 2 mm.
+constexpr int DIR_BITS = 8, DIR_N = 1 << DIR_BITS, DIR_HALF = DIR_N / 2;
+constexpr size_t DIR_CELLS = (size_t)DIR_N * DIR_N * DIR_N;
+__host__ __device__ __forceinline__ bool dir_inside(int bx, int by, int bz) {
+    return ((((unsigned)(bx + DIR_HALF)) | ((unsigned)(by + DIR_HALF)) | ((unsigned)(bz + DIR_HALF))) >> DIR_BITS) == 0u;
+}
+__host__ __device__ __forceinline__ unsigned int dir_index(int bx, int by, int bz) {   // only for blocks inside the window
+    const unsigned int ux = (unsigned)(bx + DIR_HALF), uy = (unsigned)(by + DIR_HALF), uz = (unsigned)(bz + DIR_HALF);
+    return ((uz >> 1) << (2 * DIR_BITS + 1)) | ((uy >> 1) << (DIR_BITS + 2)) | ((ux >> 2) << 4) | ((uz & 1u) << 3) | ((uy & 1u) << 2) | (ux & 3u);
+}
+
 // Voxel_s (VoxelTypes.hpp:69-92): {short sdf; uchar w_depth; pad}
 struct __align__(4) Voxel {
     short sdf;
@@ -138,6 +155,7 @@ struct tfb_ctx {
     unsigned int* claim_key;   // per slot, 0 = unclaimed
     int* claimed;              // compact list of claimed slots
     unsigned int* bucket_bits; // 1 bit per bucket: head entry allocated (empty-space skipping without touching the table)
+    int2* block_dir;           // dense directory of the blocks around the origin, {slot, ptr} per block or {-1, -1}: see BlockDir
     // render state
     int* vis_type;             // per slot (reference: uchar entriesVisibleType)
     int* vis_list[2];          // double-buffered visibleEntryIDs; DevState::cur_list says which is current
@@ -268,6 +286,7 @@ int launch_icp_all_ext(tfb_ctx* c, int levels, const float* const* vcurr, const 
 int launch_pose_set(tfb_ctx* c, const float* pose_row_major_host, bool is_w2c);
 // scene
 int launch_reset_scene(tfb_ctx* c);
+int launch_dir_rebuild(tfb_ctx* c);
 int launch_allocate(tfb_ctx* c, const float* dists);
 int launch_integrate(tfb_ctx* c, const float* dists);
 int launch_rebuild_visible(tfb_ctx* c);

@@ -277,6 +277,7 @@ static int scene_load_impl(tfb_ctx* c, const char* path) {
     if (r) return r;
     TFB_CUDA(c, cudaMemcpy(c->table, table.data(), table.size() * sizeof(HashEntry), cudaMemcpyHostToDevice));
     TFB_CUDA(c, cudaMemcpy(c->bucket_bits, bits.data(), bits.size() * sizeof(unsigned int), cudaMemcpyHostToDevice));
+    if ((r = launch_dir_rebuild(c))) return r;
     // block k went to pool slot nbl-1-k: upload the pool tail in one piece, reversed block order
     {
         std::vector<unsigned int> rev(pool.size());
