@@ -489,14 +489,19 @@ def main():
         roof["traffic_source"] = tr["source"]
     except Exception:
         pass
-    # also report the bandwidth kernels the north star names
+    # also report the bandwidth kernels the north star names, each with the DRAM traffic ncu measured for it on this frame
     extra = {}
-    for k in ("k_integrate", "k_raycast", "k_icp_all"):
+    try:
+        ncu_tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        ncu_tr = {}
+    for k in ("k_integrate", "k_raycast", "k_icp_all", "k_bilateral"):
         if k in table:
             b = algorithmic_bytes(k, cols, rows, nvis_avg)
             if b:
                 g = b / (table[k]["us_per_launch"] * 1e-6) / 1e9
-                extra[k] = {"achieved_gbs": g, "frac": g / peak, "us_per_launch": table[k]["us_per_launch"], "bytes": b}
+                extra[k] = {"bound": "hbm", "achieved": g, "achieved_gbs": g, "peak": peak, "unit": "GB/s", "frac": g / peak,
+                            "us_per_launch": table[k]["us_per_launch"], "bytes": b, "traffic": ncu_tr.get("kernels", {}).get(k)}
 
     cpu = None
     if not args.no_cpu_baseline:
@@ -509,6 +514,12 @@ def main():
 
     from topfusion_b200 import multigpu
     large = multigpu.integrate_scaling_leg(0, 1)
+    # the integration kernel where bandwidth is the question (the headline frame holds ~2 000 blocks: one wave, latency bound)
+    roof_large = {"bound": "hbm", "kernel": "k_integrate", "workload": large["workload"], "achieved": large["algorithmic_gbs_all_ranks"],
+                  "peak": peak, "unit": "GB/s", "frac": large["frac_of_measured_hbm_peak_per_gpu"], "peak_source": peak_src,
+                  "us_per_launch": large["k_integrate_us_slowest_rank"],
+                  "algorithmic_bytes_per_launch": large["visible_blocks_per_frame_all_ranks"] * 4116.0,
+                  "traffic": ncu_tr.get("kernels_large_scene", {}).get("k_integrate"), "traffic_source": ncu_tr.get("source_large_scene")}
     large_720p = multigpu.integrate_scaling_leg(0, 1, frames=16, cols=1280, rows=720)
     ingest = ingest_leg(frames[:min(W + K, 100)], args.mode)
     ref_gpu = reference_gpu_leg()
@@ -539,6 +550,7 @@ def main():
         "roofline": roof,
         "cpu_baseline": cpu,
         "voxel_updates_per_s": vox / (total_ms / 1000.0),
+        "roofline_large_scene": roof_large,
         "voxel_updates_large_scene": large,
         "voxel_updates_large_scene_1280x720": large_720p,
         "other_modes": other,

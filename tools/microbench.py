@@ -24,11 +24,12 @@ def peak():
         return 6650.0
 
 
-def run(capi, depth, poses, intr, voxel, mu, frames, warm, flush, depth_cutoff_mm, ieee=0):
+def run(capi, depth, poses, intr, voxel, mu, frames, warm, flush, depth_cutoff_mm, ieee=0, shard=None):
     rows, cols = depth.shape[1:]
     ctx = capi.Context(cols=cols, rows=rows, fx=intr[0], fy=intr[1], cx=intr[2], cy=intr[3], voxel_size=voxel, mu=mu,
                        num_blocks=1 << 20, num_buckets=1 << 22, excess_size=1 << 19, depth_cutoff_mm=depth_cutoff_mm, ieee_arith=ieee,
-                       view_frustum_max=max(3.0, depth_cutoff_mm / 1000.0 + 2 * mu))
+                       view_frustum_max=max(3.0, depth_cutoff_mm / 1000.0 + 2 * mu),
+                       **({"shard_count": shard[0], "shard_rank": shard[1]} if shard else {}))
     L = ctx.L
     n = depth.shape[0]
     dev = [ctx.upload(depth[i]) for i in range(n)]
@@ -47,17 +48,20 @@ def run(capi, depth, poses, intr, voxel, mu, frames, warm, flush, depth_cutoff_m
             ctx.ktiming(True)
         c2w = np.ascontiguousarray(poses[fi], dtype=np.float32)
         w2c = np.ascontiguousarray(np.linalg.inv(poses[fi]), dtype=np.float32)
+        if flush == "frame":   # cold at the start of the frame: the voxels come from HBM, what the frame's own stages produce stays in L2
+            ctx.flush_l2()
         ctx._ck(L.tfb_compute_dists(ctx.h, dev[fi].ptr, dists.ptr, C.c_int(cols), C.c_int(rows)))
         ctx._ck(L.tfb_allocate_scene_from_depth(ctx.h, w2c.ctypes.data_as(C.c_void_p), dists.ptr))
-        if flush:
+        if flush is True:
             ctx.flush_l2()
         ctx._ck(L.tfb_integrate_into_scene(ctx.h, w2c.ctypes.data_as(C.c_void_p), dists.ptr))
         if t >= warm:
             nblk.append(ctx.voxel_updates() / 512.0)
-        ctx._ck(L.tfb_create_expected_depths(ctx.h, w2c.ctypes.data_as(C.c_void_p)))
-        if flush:
-            ctx.flush_l2()
-        ctx._ck(L.tfb_create_icp_maps(ctx.h, c2w.ctypes.data_as(C.c_void_p), pts.ptr, nrm.ptr))
+        if not shard:   # one rank of a sharded scene alone: allocation + integration only (the raycast reads the other ranks)
+            ctx._ck(L.tfb_create_expected_depths(ctx.h, w2c.ctypes.data_as(C.c_void_p)))
+            if flush is True:
+                ctx.flush_l2()
+            ctx._ck(L.tfb_create_icp_maps(ctx.h, c2w.ctypes.data_as(C.c_void_p), pts.ptr, nrm.ptr))
         ctx.sync()
     kt = ctx.kernel_times()
     cnt = ctx.counters()
@@ -90,8 +94,11 @@ def main():
     ap.add_argument("--seq", default="S1")
     ap.add_argument("--seq-frames", type=int, default=40)
     ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--flush-frame", action="store_true", help="flush L2 once per frame (before the allocation stage) instead of in front of every timed kernel")
     ap.add_argument("--out", default=None)
     ap.add_argument("--ieee", type=int, default=0, help="1: IEEE integration arithmetic (tfb_params.ieee_arith)")
+    ap.add_argument("--shard", type=int, nargs=2, default=None, metavar=("COUNT", "RANK"),
+                    help="time ONE rank of a scene sharded COUNT ways on this GPU (allocation + integration only)")
     a = ap.parse_args()
     from topfusion_b200 import capi, synth
     depth, poses, intr = synth.sequence(a.seq, a.seq_frames)
@@ -99,9 +106,10 @@ def main():
     res = []
     for v in a.voxel_mm:
         for m in a.mu_voxels:
-            r = run(capi, depth, poses, intr, v / 1000.0, m * v / 1000.0, a.frames, a.warmup, not a.no_flush, cutoff, a.ieee)
+            r = run(capi, depth, poses, intr, v / 1000.0, m * v / 1000.0, a.frames, a.warmup, ("frame" if a.flush_frame else not a.no_flush), cutoff, a.ieee, a.shard)
             res.append(r)
-            ki, kr = r["kernels"]["k_integrate"], r["kernels"]["k_raycast"]
+            ki = r["kernels"]["k_integrate"]
+            kr = r["kernels"].get("k_raycast", {"us_per_launch": 0.0, "gbs": 0.0, "frac_of_measured_hbm_peak": 0.0})
             print(f"{a.seq} voxel {v} mm mu {m * v} mm: {r['visible_blocks_avg']:.0f} blocks | integrate {ki['us_per_launch']:.1f} us "
                   f"{ki['gbs']:.0f} GB/s ({100 * ki['frac_of_measured_hbm_peak']:.1f} %) {r['voxel_updates_per_s'] / 1e9:.1f} G upd/s | "
                   f"raycast {kr['us_per_launch']:.1f} us {kr['gbs']:.0f} GB/s ({100 * kr['frac_of_measured_hbm_peak']:.1f} %)", flush=True)

@@ -34,14 +34,4 @@ print("per-SM span us: mean %.1f min %.1f max %.1f" % (busy.mean(), busy.min(), 
 for t in range(0, int((end_ns.max() - t0) / 1000) + 5, 5):
     tt = t0 + t * 1000
     print("t=%3d us resident warps %5d" % (t, int(((start_ns <= tt) & (end_ns > tt)).sum())))
-out2 = np.zeros(8 * 16384, np.int64)
-if ctx.L.tfb_debug_ray_profile2(out2.ctypes.data_as(C.c_void_p), C.c_int(out2.size)) == 0:
-    q = out2.reshape(-1, 8)[:9600].astype(np.float64)
-    names = ["setup", "read", "mark", "trilinear", "final"]
-    tot = q[:, :5].sum()
-    print("lane-0 cycle split over all warps: " + ", ".join(f"{n} {100 * q[:, i].sum() / tot:.0f}%" for i, n in enumerate(names)))
-    for w in order[:6]:
-        it = max(q[w, 5], 1)
-        print(f"warp {w}: iter {int(q[w,5])} miss {int(q[w,6])} | us: " + ", ".join(f"{n} {q[w, i] / 1965:.1f}" for i, n in enumerate(names))
-              + f" | read/iter {q[w,1] / it:.0f} cyc, mark/iter {q[w,2] / max(q[w,5]-q[w,6],1):.0f}, tri/iter {q[w,3] / max(q[w,5]-q[w,6],1):.0f}")
 ctx.close()
