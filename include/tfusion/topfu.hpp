@@ -105,6 +105,10 @@ public:
     void renderPointCloud(cuda::DeviceArray<float>& points4, int& count, bool skipPoints = false);
     void saveScene(const std::string& path);
     void loadScene(const std::string& path);
+    // block streaming (the reference's dormant swapping, GlobalCache.hpp / Scene(..., useSwapping)): blocks that left the enlarged
+    // frustum go to host memory, blocks the (predicted) pose looks at come back; returns the number of blocks moved
+    int streamOut(int maxBlocks = 0);
+    int streamIn(bool everything = false);
 
 private:
     TopFu(const TopFu&);

@@ -245,6 +245,22 @@ TFB_API int tfb_render_point_cloud(tfb_ctx* c, const float* pose_c2w_or_null, in
 TFB_API int tfb_scene_save(tfb_ctx* c, const char* path);
 TFB_API int tfb_scene_load(tfb_ctx* c, const char* path);
 
+/* Block streaming between the voxel pool and host memory, for scenes larger than the pool.  Replaces the reference's host swap
+ * cache and its kernels, which the reference never switches on: GlobalCache (tfusion/include/tfusion/GlobalCache.hpp:14-135),
+ * reAllocateSwappedOutVoxelBlocks_device (tfusion/src/cuda/SceneReconstructionEngine_host.cu:417-432), the enlarged frustum of
+ * checkPointVisibility<true> (tfusion/include/tfusion/cuda/SceneReconstructionEngine.hpp:315-322), Scene(..., useSwapping)
+ * (tfusion/src/topfu.cpp:67).  Synchronous calls between frames; not for a sharded context.
+ * tfb_stream_out: moves up to max_blocks (<= 0: all) resident blocks that are not visible in the current frame and lie outside the
+ *   enlarged frustum (image widened by 1/8 per side) of the current pose into the host store; their pool slots are free again and
+ *   their hash entries carry ptr = -1, which the integration skips and the raycast reads as empty space, as in the reference.
+ * tfb_stream_in: brings back the stored blocks inside the enlarged frustum of pose_w2c (row-major world->camera; NULL: the current
+ *   pose), or every stored block when all != 0.  A block that finds no free pool slot stays in the store (*n_left_in_store).
+ *   Restoring before the frame that looks at a block makes the scene identical to one that was never streamed.
+ * tfb_reset drops the store; tfb_scene_save fails with TFB_ERR_STATE while blocks are out. */
+TFB_API int tfb_stream_out(tfb_ctx* c, int max_blocks, int* n_out);
+TFB_API int tfb_stream_in(tfb_ctx* c, const float* pose_w2c_or_null, int all, int* n_in, int* n_left_in_store);
+TFB_API int tfb_stream_stats(tfb_ctx* c, long long* blocks_in_pool, long long* blocks_in_store);
+
 /* ---- inspection (tests, bench, debug dumps) ---------------------------------------------- */
 /* out[8] = n_visible, last_free_block, last_free_excess, n_new_this_frame, frame_counter, resets,
  *          n_raycast_extras, n_allocated */

@@ -120,6 +120,18 @@ void TopFu::renderPointCloud(cuda::DeviceArray<float>& points4, int& count, bool
 
 void TopFu::saveScene(const std::string& path) { TF_CHECK(tfb_scene_save(ctx_, path.c_str())); }
 
+int TopFu::streamOut(int maxBlocks) {
+    int n = 0;
+    TF_CHECK(tfb_stream_out(ctx_, maxBlocks, &n));
+    return n;
+}
+
+int TopFu::streamIn(bool everything) {
+    int n = 0;
+    TF_CHECK(tfb_stream_in(ctx_, 0, everything ? 1 : 0, &n, 0));
+    return n;
+}
+
 void TopFu::loadScene(const std::string& path) {
     TF_CHECK(tfb_scene_load(ctx_, path.c_str()));
     frame_counter_ = tfb_num_poses(ctx_);

@@ -14,7 +14,8 @@ WANT = ["Kernel Name", "launch__grid_size", "launch__block_size", "launch__regis
         "launch__waves_per_multiprocessor", "launch__occupancy_limit_registers", "launch__occupancy_limit_warps",
         "smsp__inst_executed.sum", "sm__inst_executed_pipe_xu.sum", "sm__inst_executed_pipe_fma.sum", "sm__inst_executed_pipe_alu.sum",
         "sm__inst_executed_pipe_lsu.sum", "sm__pipe_xu_cycles_active.avg.pct_of_peak_sustained_active",
-        "lts__t_sectors_op_atom.sum", "lts__t_sectors_op_red.sum", "l1tex__t_set_accesses_pipe_lsu_mem_global_op_atom.sum",
+        "lts__t_sectors_op_atom.sum", "lts__t_sectors_op_red.sum", "l1tex__m_l1tex2xbar_write_sectors_mem_global_op_atom.sum",
+        "l1tex__m_l1tex2xbar_write_sectors_mem_global_op_red.sum", "lts__t_sectors_srcunit_tex_op_atom.sum", "lts__t_sectors_srcunit_tex_op_red.sum", "l1tex__t_set_accesses_pipe_lsu_mem_global_op_atom.sum",
         "l1tex__t_set_accesses_pipe_lsu_mem_global_op_red.sum", "lts__t_bytes.sum", "l1tex__t_bytes.sum",
         "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct", "smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct",
         "smsp__warp_issue_stalled_math_pipe_throttle_per_warp_active.pct", "smsp__warp_issue_stalled_barrier_per_warp_active.pct",

@@ -101,6 +101,9 @@ def lib() -> C.CDLL:
             "tfb_render_point_cloud": [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)],
             "tfb_scene_save": [C.c_void_p, C.c_char_p],
             "tfb_scene_load": [C.c_void_p, C.c_char_p],
+            "tfb_stream_out": [C.c_void_p, C.c_int, C.POINTER(C.c_int)],
+            "tfb_stream_in": [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)],
+            "tfb_stream_stats": [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)],
             "tfb_shard_push_frame": [C.c_void_p, C.c_void_p],
             "tfb_process_frame_sharded": [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)],
             "tfb_shard_barrier": [C.c_void_p],
@@ -358,6 +361,28 @@ class Context:
 
     def load_scene(self, path: str):
         self._ck(self.L.tfb_scene_load(self.h, path.encode()))
+
+    # -- block streaming between the voxel pool and host memory (tfb_stream_*, include/tfusion_b200.h) --
+    def stream_out(self, max_blocks: int = 0) -> int:
+        n = C.c_int(0)
+        self._ck(self.L.tfb_stream_out(self.h, C.c_int(max_blocks), C.byref(n)))
+        return n.value
+
+    def stream_in(self, pose_w2c=None, all_blocks: bool = False):
+        """returns (blocks restored, blocks left in the host store)"""
+        n, left = C.c_int(0), C.c_int(0)
+        p = None
+        if pose_w2c is not None:
+            m = np.ascontiguousarray(pose_w2c, dtype=np.float32)
+            p = m.ctypes.data_as(C.c_void_p)
+        self._ck(self.L.tfb_stream_in(self.h, p, C.c_int(1 if all_blocks else 0), C.byref(n), C.byref(left)))
+        return n.value, left.value
+
+    def stream_stats(self):
+        """(blocks in the pool, blocks in the host store)"""
+        a, b = C.c_longlong(0), C.c_longlong(0)
+        self._ck(self.L.tfb_stream_stats(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     # -- frames ----------------------------------------------------------------------------------------
     def process_frame(self, depth) -> bool:

@@ -58,6 +58,7 @@ template <typename T>
 cudaError_t dmalloc(T** p, size_t n) { return cudaMalloc((void**)p, n * sizeof(T)); }
 
 void free_all(tfb_ctx* c) {
+    stream_store_free(c);
     cudaFree(c->table); cudaFree(c->vba); cudaFree(c->vba_free); cudaFree(c->excess_free);
     cudaFree(c->claim_key); cudaFree(c->claimed); cudaFree(c->bucket_bits); cudaFree(c->block_dir); cudaFree(c->vis_type); cudaFree(c->vis_list[0]); cudaFree(c->vis_list[1]); cudaFree(c->cache_pool); cudaFree(c->cache_tag);
     cudaFree(c->minmax); cudaFree(c->raycast); cudaFree(c->dists_buf[0]); cudaFree(c->dists_buf[1]); cudaFree(c->depth_in); cudaFree(c->icp_partial);
@@ -129,6 +130,7 @@ int do_reset(tfb_ctx* c) {
     if (r) return r;
     r = launch_reset_scene(c);
     if (r) return r;
+    stream_store_clear(c);   // the scene is gone, and so is what was streamed out of it
     next_cache_epoch(c);   // sharded scene: no copy of a foreign block outlives the scene
     return launch_pose_set(c, IDENTITY, false);
 }

@@ -155,6 +155,7 @@ struct tfb_ctx {
     unsigned int* claim_key;   // per slot, 0 = unclaimed
     int* claimed;              // compact list of claimed slots
     unsigned int* bucket_bits; // 1 bit per bucket: head entry allocated (empty-space skipping without touching the table)
+    struct HostBlockStore* store;   // blocks streamed out to the host (tfb_stream_out / tfb_stream_in), created on first use
     int2* block_dir;           // dense directory of the blocks around the origin, {slot, ptr} per block or {-1, -1}: see BlockDir
     // render state
     int* vis_type;             // per slot (reference: uchar entriesVisibleType)
@@ -287,6 +288,11 @@ int launch_pose_set(tfb_ctx* c, const float* pose_row_major_host, bool is_w2c);
 // scene
 int launch_reset_scene(tfb_ctx* c);
 int launch_dir_rebuild(tfb_ctx* c);
+int launch_stream_select(tfb_ctx* c, int mode, const float* pose_w2c_rowmajor, int* list_dev, int cap, int* counter_dev);
+int launch_stream_evict(tfb_ctx* c, const int* list_dev, int n, void* xfer_dev);
+int launch_stream_restore(tfb_ctx* c, const int* list_dev, int n, const void* xfer_dev, int* restored_dev);
+void stream_store_clear(tfb_ctx* c);   // tfb_export.cu: the host side of the block streaming
+void stream_store_free(tfb_ctx* c);
 int launch_allocate(tfb_ctx* c, const float* dists);
 int launch_integrate(tfb_ctx* c, const float* dists);
 int launch_rebuild_visible(tfb_ctx* c);

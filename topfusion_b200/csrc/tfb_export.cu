@@ -14,6 +14,22 @@
 #include <vector>
 
 #include "tfb_common.cuh"
+#include <unordered_map>
+
+// Host side of the block streaming (tfb_stream_out / tfb_stream_in): GlobalCache restated (GlobalCache.hpp:14-135 keeps one 2 KB
+// slot per hash entry, 2.4 GB for the default table; here blocks are stored where they arrive and found through a map).
+struct HostBlockStore {
+    std::unordered_map<int, size_t> where;      // hash entry -> index of its 2 KB in `data`
+    std::vector<unsigned int> data;             // BLOCK3 words per stored block
+    std::vector<size_t> free_slots;
+    int* list_dev = nullptr;                    // transfer: entry ids, success flags, counter, blocks
+    int* flag_dev = nullptr;
+    int* counter_dev = nullptr;
+    unsigned int* xfer_dev = nullptr;
+    unsigned int* xfer_host = nullptr;          // pinned
+    int* list_host = nullptr;                   // pinned: ids + flags + counter
+    static constexpr int CHUNK = 8192;          // blocks per transfer (16 MB; the reference's SDF_TRANSFER_BLOCK_NUM is 0x1000)
+};
 
 namespace tfb {
 
@@ -174,6 +190,8 @@ struct SceneFileHeader {
 static int scene_save_impl(tfb_ctx* c, const char* path) {
     int r = tfb_sync(c);
     if (r) return r;
+    if (c->store && !c->store->where.empty())
+        return set_err(c, TFB_ERR_STATE, "tfb_scene_save: blocks are streamed out to the host; call tfb_stream_in(c, NULL, 1, ...) first");
     std::vector<HashEntry> table((size_t)c->total_entries);
     TFB_CUDA(c, cudaMemcpy(table.data(), c->table, table.size() * sizeof(HashEntry), cudaMemcpyDeviceToHost));
     std::vector<int> used;
@@ -331,4 +349,138 @@ int tfb_scene_load(tfb_ctx* c, const char* path) {
     }
 }
 
+// ---- block streaming (device side and reference citations in tfb_scene.cu) ----
+static int stream_prepare(tfb_ctx* c) {
+    if (c->p.shard_count > 1) return set_err(c, TFB_ERR_STATE, "block streaming: not for a sharded context (ptr = -1 means \"held by another rank\" there)");
+    if (c->store) return TFB_OK;
+    HostBlockStore* st = new (std::nothrow) HostBlockStore();
+    if (!st) return set_err(c, TFB_ERR_NOMEM, "block streaming: host store");
+    const int n = HostBlockStore::CHUNK;
+    bool ok = cudaMalloc((void**)&st->list_dev, n * sizeof(int)) == cudaSuccess && cudaMalloc((void**)&st->flag_dev, n * sizeof(int)) == cudaSuccess &&
+              cudaMalloc((void**)&st->counter_dev, sizeof(int)) == cudaSuccess &&
+              cudaMalloc((void**)&st->xfer_dev, (size_t)n * BLOCK3 * sizeof(unsigned int)) == cudaSuccess &&
+              cudaMallocHost((void**)&st->xfer_host, (size_t)n * BLOCK3 * sizeof(unsigned int)) == cudaSuccess &&
+              cudaMallocHost((void**)&st->list_host, (2 * n + 1) * sizeof(int)) == cudaSuccess;
+    c->store = st;
+    if (!ok) { stream_store_free(c); return set_err(c, TFB_ERR_NOMEM, "block streaming: transfer buffers"); }
+    return TFB_OK;
+}
+
+static int stream_out_impl(tfb_ctx* c, int max_blocks, int* n_out) {
+    int r = tfb_sync(c);
+    if (r || (r = stream_prepare(c))) return r;
+    HostBlockStore* st = c->store;
+    const int N = HostBlockStore::CHUNK;
+    int done = 0;
+    for (;;) {
+        const int want = max_blocks > 0 ? (max_blocks - done < N ? max_blocks - done : N) : N;
+        if (want <= 0) break;
+        if ((r = launch_stream_select(c, 0, c->hs->pose_w2c, st->list_dev, want, st->counter_dev))) return r;
+        TFB_CUDA(c, cudaMemcpyAsync(st->list_host + 2 * N, st->counter_dev, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        TFB_CUDA(c, cudaStreamSynchronize(c->stream));
+        const int found = st->list_host[2 * N];
+        const int n = found < want ? found : want;
+        if (n == 0) break;
+        if ((r = launch_stream_evict(c, st->list_dev, n, st->xfer_dev))) return r;
+        TFB_CUDA(c, cudaMemcpyAsync(st->list_host, st->list_dev, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        TFB_CUDA(c, cudaMemcpyAsync(st->xfer_host, st->xfer_dev, (size_t)n * BLOCK3 * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+        TFB_CUDA(c, cudaStreamSynchronize(c->stream));
+        for (int i = 0; i < n; ++i) {
+            size_t at;
+            if (!st->free_slots.empty()) { at = st->free_slots.back(); st->free_slots.pop_back(); }
+            else { at = st->data.size() / BLOCK3; st->data.resize(st->data.size() + BLOCK3); }
+            memcpy(&st->data[at * BLOCK3], st->xfer_host + (size_t)i * BLOCK3, BLOCK3 * sizeof(unsigned int));
+            st->where[st->list_host[i]] = at;
+        }
+        done += n;
+        if (found <= want) break;   // the sweep found no more than fitted
+    }
+    if (n_out) *n_out = done;
+    return TFB_OK;
+}
+
+static int stream_in_impl(tfb_ctx* c, const float* pose_w2c, int all, int* n_in, int* n_left) {
+    int r = tfb_sync(c);
+    if (r || (r = stream_prepare(c))) return r;
+    HostBlockStore* st = c->store;
+    const int N = HostBlockStore::CHUNK;
+    int done = 0;
+    bool pool_full = false;
+    while (!st->where.empty() && !pool_full) {
+        if ((r = launch_stream_select(c, all ? 2 : 1, pose_w2c ? pose_w2c : c->hs->pose_w2c, st->list_dev, N, st->counter_dev))) return r;
+        TFB_CUDA(c, cudaMemcpyAsync(st->list_host + 2 * N, st->counter_dev, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        TFB_CUDA(c, cudaMemcpyAsync(st->list_host, st->list_dev, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        TFB_CUDA(c, cudaStreamSynchronize(c->stream));
+        const int found = st->list_host[2 * N];
+        const int n = found < N ? found : N;
+        if (n == 0) break;
+        for (int i = 0; i < n; ++i) {
+            auto it = st->where.find(st->list_host[i]);
+            if (it == st->where.end()) return set_err(c, TFB_ERR_STATE, "block streaming: an entry is marked swapped out but the host store does not hold it");
+            memcpy(st->xfer_host + (size_t)i * BLOCK3, &st->data[it->second * BLOCK3], BLOCK3 * sizeof(unsigned int));
+        }
+        TFB_CUDA(c, cudaMemcpyAsync(st->xfer_dev, st->xfer_host, (size_t)n * BLOCK3 * sizeof(unsigned int), cudaMemcpyHostToDevice, c->stream));
+        if ((r = launch_stream_restore(c, st->list_dev, n, st->xfer_dev, st->flag_dev))) return r;
+        TFB_CUDA(c, cudaMemcpyAsync(st->list_host + N, st->flag_dev, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        TFB_CUDA(c, cudaStreamSynchronize(c->stream));
+        for (int i = 0; i < n; ++i) {
+            if (!st->list_host[N + i]) { pool_full = true; continue; }   // no pool slot: stays in the store
+            auto it = st->where.find(st->list_host[i]);
+            st->free_slots.push_back(it->second);
+            st->where.erase(it);
+            ++done;
+        }
+        if (found <= N) break;
+    }
+    if (n_in) *n_in = done;
+    if (n_left) *n_left = (int)st->where.size();
+    return TFB_OK;
+}
+
+int tfb_stream_out(tfb_ctx* c, int max_blocks, int* n_out) {
+    if (!c) return TFB_ERR_ARG;
+    try {
+        return stream_out_impl(c, max_blocks, n_out);
+    } catch (const std::bad_alloc&) {
+        return set_err(c, TFB_ERR_NOMEM, "tfb_stream_out: out of host memory");
+    } catch (...) {
+        return set_err(c, TFB_ERR_STATE, "tfb_stream_out: unexpected failure");
+    }
+}
+int tfb_stream_in(tfb_ctx* c, const float* pose_w2c_or_null, int all, int* n_in, int* n_left_in_store) {
+    if (!c) return TFB_ERR_ARG;
+    try {
+        return stream_in_impl(c, pose_w2c_or_null, all, n_in, n_left_in_store);
+    } catch (const std::bad_alloc&) {
+        return set_err(c, TFB_ERR_NOMEM, "tfb_stream_in: out of host memory");
+    } catch (...) {
+        return set_err(c, TFB_ERR_STATE, "tfb_stream_in: unexpected failure");
+    }
+}
+int tfb_stream_stats(tfb_ctx* c, long long* blocks_in_pool, long long* blocks_in_store) {
+    if (!c) return TFB_ERR_ARG;
+    int r = tfb_sync(c);
+    if (r) return r;
+    DevState st;
+    TFB_CUDA(c, cudaMemcpy(&st, c->ds, sizeof(st), cudaMemcpyDeviceToHost));
+    if (blocks_in_pool) *blocks_in_pool = (long long)c->p.num_blocks - 1 - st.last_free_block;
+    if (blocks_in_store) *blocks_in_store = c->store ? (long long)c->store->where.size() : 0;
+    return TFB_OK;
+}
+
 }  // extern "C"
+
+void tfb::stream_store_clear(tfb_ctx* c) {
+    if (!c->store) return;
+    c->store->where.clear(); c->store->data.clear(); c->store->free_slots.clear();
+}
+void tfb::stream_store_free(tfb_ctx* c) {
+    if (!c->store) return;
+    HostBlockStore* st = c->store;
+    cudaFree(st->list_dev); cudaFree(st->flag_dev); cudaFree(st->counter_dev); cudaFree(st->xfer_dev);
+    if (st->xfer_host) cudaFreeHost(st->xfer_host);
+    if (st->list_host) cudaFreeHost(st->list_host);
+    delete st;
+    c->store = nullptr;
+}
+
