@@ -122,3 +122,36 @@ def test_config4_large_scene_2mm_sharded_bit_exact(gpu):
         for c in reversed(ctxs):
             c.close()
         o.close()
+
+
+def test_blocks_outside_the_directory_window_bit_exact(gpu, s1_frames):
+    """The block directory covers 256^3 blocks around the origin; the hash serves the rest.  At 1.5 mm voxels a block is 12 mm and
+    the window ends 1.536 m from the origin — in the middle of the S1 scene (sphere at 0.85–1.55 m, floor beyond), so the march
+    crosses the window's edge, trilinear reads straddle it, and most of the floor is resolved through the table.  Everything must
+    still be bit-identical to the oracle: rays, maps, visible set, voxels."""
+    from oracle import tfo
+    depth, poses, _ = s1_frames
+    kw = dict(voxel_size=0.0015, mu=0.006, num_blocks=1 << 18, num_buckets=1 << 21, excess_size=1 << 18)
+    L = tfo.Lib("port")
+    o = tfo.Oracle(lib=L, **kw)
+    g = gpu.Context(ieee_arith=1, **kw)
+    try:
+        for i in range(2):
+            dists = L.compute_dists(depth[i], 2047)
+            c2w = poses[i].astype(np.float32)
+            w2c = L.pose_inv(c2w)
+            o.allocate(w2c, dists); g.allocate(w2c, dists)
+            o.integrate(w2c, dists); g.integrate(w2c, dists)
+            assert o.voxel_updates() == g.voxel_updates() > 512 * 10000, i
+            o.expected_depths(w2c); g.expected_depths(w2c)
+            (op, on), (gp, gn) = o.icp_maps(c2w), g.icp_maps(c2w)
+            assert np.array_equal(o.raycast_result().view(np.uint32), g.raycast_result().view(np.uint32)), i
+            assert same_bits_nan(op, gp).all() and same_bits_nan(on, gn).all(), i
+        to, tg = o.table(), g.table()
+        pos = tg[tg["ptr"] >= 0]["pos"].astype(np.int64)
+        inside = (np.abs(pos + 0.5) < 128).all(axis=1)
+        assert 0.05 < inside.mean() < 0.95, inside.mean()      # both sides of the window's edge are populated
+        assert tfo.allocated_set(to) == gpu.allocated_set(tg)
+        assert tfo.visible_set(to, o.visible_ids()) == gpu.visible_set(tg, g.visible_ids())
+    finally:
+        g.close(); o.close()

@@ -89,3 +89,32 @@ def test_sharded_context_refuses_the_unsharded_entry(gpu, s1_frames):
             c.frame_raycast()
     finally:
         c.close()
+
+
+def test_sharded_scene_outside_the_directory_window(gpu, s1_frames):
+    """the same at 1.5 mm voxels, where half the scene lies outside the block directory's window and is served by the hash —
+    local blocks, this frame's copies of foreign blocks and the owner's pool alike"""
+    depth, _, _ = s1_frames
+    kw = dict(corrected_mode=1, voxel_size=0.0015, mu=0.006, num_blocks=1 << 18, num_buckets=1 << 21, excess_size=1 << 18)
+    single = gpu.Context(**kw)
+    ctxs = make_shards(gpu, 2, **kw)
+    try:
+        for i in range(3):
+            buf = ctxs[0].upload(depth[i], "frame")
+            oks = sharded_frame(ctxs, buf)
+            ok1 = single.process_frame(depth[i])
+            assert all(o == ok1 for o in oks), (i, oks, ok1)
+            for c in ctxs:
+                assert np.array_equal(c.pose().view(np.uint32), single.pose().view(np.uint32)), f"frame {i}: pose differs"
+            assert sum(c.voxel_updates() for c in ctxs) == single.voxel_updates(), i
+            if i > 0:
+                r1 = single.raycast_result()
+                for c in ctxs:
+                    assert np.array_equal(c.raycast_result().view(np.uint32), r1.view(np.uint32)), f"frame {i}: raycast differs"
+        t1 = single.table()
+        for c in ctxs:
+            assert gpu.visible_set(c.table(), c.visible_ids()) == gpu.visible_set(t1, single.visible_ids())
+    finally:
+        for c in reversed(ctxs):
+            c.close()
+        single.close()
