@@ -26,4 +26,19 @@ if ctx.L.tfb_debug_icp_cta(cta.ctypes.data_as(C.c_void_p)) == 0:
         print("  %-12s min %5.2f  median %5.2f  p90 %5.2f  max %5.2f (CTA %d)" % (name, t[:, col].min(), np.median(t[:, col]), np.percentile(t[:, col], 90), t[:, col].max(), int(t[:, col].argmax())))
     d = t[:, 1] - t[:, 0]
     print("  pixel phase per CTA: min %.2f median %.2f max %.2f; slowest CTAs:" % (d.min(), np.median(d), d.max()), np.argsort(-d)[:8].tolist())
+pix = np.zeros(256 * 24, np.int32)
+if hasattr(ctx.L, "tfb_debug_icp_pix") and ctx.L.tfb_debug_icp_pix(pix.ctypes.data_as(C.c_void_p)) == 0:
+    p = pix.reshape(256, 24)[:148]
+    sm, nl, cyc = p[:, 0], p[:, 1], p[:, 2:21].astype(np.float64)
+    us = cyc / 1965.0
+    print("pixel phase per CTA (clock64 of thread 0), level-0 iterations 9..18: median %.2f us, p90 %.2f, max %.2f" % (np.median(us[:, 9:]), np.percentile(us[:, 9:], 90), us[:, 9:].max()))
+    print("list length at level 0: min %d median %d max %d" % (nl.min(), np.median(nl), nl.max()))
+    slow = np.argsort(-us[:, 9:].mean(axis=1))[:10]
+    for c in slow:
+        print("  CTA %3d SM %3d list %4d : " % (c, sm[c], nl[c]) + " ".join("%.2f" % v for v in us[c, 9:]))
+    # is slowness a property of the CTA (persistent) or of the iteration (random)?
+    r = np.corrcoef(us[:, 10], us[:, 15])[0, 1]
+    print("correlation of a CTA's pixel time between iterations 10 and 15: %.2f; with its list length: %.2f" % (r, np.corrcoef(us[:, 9:].mean(axis=1), nl)[0, 1]))
+    print("per-iteration max over CTAs: " + " ".join("%.2f" % v for v in us.max(axis=0)))
+    print("per-iteration median       : " + " ".join("%.2f" % v for v in np.median(us, axis=0)))
 ctx.close()

@@ -474,7 +474,9 @@ __device__ __forceinline__ void st_partial(unsigned long long* p, unsigned long 
 #ifdef TFB_ICP_PROFILE
 __device__ long long g_icp_prof[64 * 8];
 __device__ long long g_icp_cta[256 * 4];   // iteration 12 (level 0): per CTA globaltimer at pixel start, pixel end, row stored, fold done
-#define ICP_STAMP(slot) do { if (blockIdx.x == 0 && tid == 0 && iter_global < 64) g_icp_prof[iter_global * 8 + (slot)] = clock64(); \
+__device__ int g_icp_pix[256 * 24];        // per CTA: SM id, list length at level 0, then per iteration 0..18 the cycles of its pixel phase (clock64 of thread 0)
+#define ICP_STAMP(slot) do { if (tid == 0 && blockIdx.x < 256 && iter_global < 19) { if ((slot) == 0) pix_t0 = clock64(); if ((slot) == 1) g_icp_pix[blockIdx.x * 24 + 2 + iter_global] = (int)(clock64() - pix_t0); } \
+    if (blockIdx.x == 0 && tid == 0 && iter_global < 64) g_icp_prof[iter_global * 8 + (slot)] = clock64(); \
     if (iter_global == 12 && tid == 0 && blockIdx.x < 256 && ((slot) == 0 || (slot) == 1 || (slot) == 2 || (slot) == 4)) { long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); \
         g_icp_cta[blockIdx.x * 4 + ((slot) == 0 ? 0 : (slot) == 1 ? 1 : (slot) == 2 ? 2 : 3)] = gt; } } while (0)
 #else
@@ -572,6 +574,10 @@ __global__ void __launch_bounds__(ICPA_THREADS, 1)
 
     int iter_global = 0;
     bool ok = true;
+#ifdef TFB_ICP_PROFILE
+    long long pix_t0 = 0;
+    if (tid == 0 && blockIdx.x < 256) { unsigned int smid; asm("mov.u32 %0, %%smid;" : "=r"(smid)); g_icp_pix[blockIdx.x * 24] = (int)smid; }
+#endif
     for (int l = a.levels - 1; l >= 0 && ok; --l) {
         const IcpLevelArgs L = a.lv[l];
         const int npx = L.w * L.h;
@@ -605,6 +611,9 @@ __global__ void __launch_bounds__(ICPA_THREADS, 1)
             }
             __syncthreads();
             n_list = s_cnt[ICP_LIST_SLOTS * ICPA_WARPS];
+#ifdef TFB_ICP_PROFILE
+            if (tid == 0 && blockIdx.x < 256 && l == 0) g_icp_pix[blockIdx.x * 24 + 1] = n_list;
+#endif
         }
         for (int it = 0; it < L.iters && ok; ++it, ++iter_global) {
             float acc[ICP_ACC];
@@ -614,11 +623,18 @@ __global__ void __launch_bounds__(ICPA_THREADS, 1)
 
             // pixels in flight per thread sized to the level: 5 at 640x480 (4.05 pixels per thread), 2 and 1 on the coarse levels
             if (n_list >= 0) {
-                const int per_thread = (n_list + ICPA_THREADS - 1) / ICPA_THREADS;
-                if (per_thread <= 1) icp_pixels<1, true>(L, a, n_list, tid, ICPA_THREADS, s_aff, acc, s_list);
-                else if (per_thread <= 2) icp_pixels<2, true>(L, a, n_list, tid, ICPA_THREADS, s_aff, acc, s_list);
-                else if (per_thread <= 3) icp_pixels<3, true>(L, a, n_list, tid, ICPA_THREADS, s_aff, acc, s_list);
-                else icp_pixels<ICPA_UNROLL, true>(L, a, n_list, tid, ICPA_THREADS, s_aff, acc, s_list);
+                // Pixels in flight per WARP: the lists of the 148 CTAs differ by +-10 % (896..1092 entries at 640x480), and a CTA
+                // whose list is a few entries past a multiple of the CTA size used to run a whole extra pixel in every thread,
+                // predicated off in all but one warp — the same dozen CTAs took 2.15 us for a pixel phase whose median is 1.18 us,
+                // in every iteration, and everybody waits for them.  A warp now runs exactly as many pixels as ITS threads have
+                // (the first rem / 32 warps one more than the others, all of them in flight at once).  Pixel -> thread assignment
+                // and the order of a thread's accumulations are unchanged, so the sums are bit-identical.
+                const int full = n_list / ICPA_THREADS, rem = n_list - full * ICPA_THREADS;
+                const int per_thread = full + ((warp * 32 < rem) ? 1 : 0);
+                if (per_thread == 1) icp_pixels<1, true>(L, a, n_list, tid, ICPA_THREADS, s_aff, acc, s_list);
+                else if (per_thread == 2) icp_pixels<2, true>(L, a, n_list, tid, ICPA_THREADS, s_aff, acc, s_list);
+                else if (per_thread == 3) icp_pixels<3, true>(L, a, n_list, tid, ICPA_THREADS, s_aff, acc, s_list);
+                else if (per_thread > 3) icp_pixels<ICPA_UNROLL, true>(L, a, n_list, tid, ICPA_THREADS, s_aff, acc, s_list);
             } else {
                 icp_pixels<ICPA_UNROLL, false>(L, a, npx, gtid, gstride, s_aff, acc, nullptr);
             }
@@ -755,6 +771,9 @@ __global__ void __launch_bounds__(ICPA_THREADS, 1)
 }
 
 #ifdef TFB_ICP_PROFILE
+extern "C" __attribute__((visibility("default"))) int tfb_debug_icp_pix(int* out6144) {
+    return cudaMemcpyFromSymbol(out6144, g_icp_pix, sizeof(int) * 256 * 24) == cudaSuccess ? 0 : -2;
+}
 extern "C" __attribute__((visibility("default"))) int tfb_debug_icp_cta(long long* out1024) {
     return cudaMemcpyFromSymbol(out1024, g_icp_cta, sizeof(long long) * 1024) == cudaSuccess ? 0 : -2;
 }
