@@ -366,16 +366,26 @@ static int stream_prepare(tfb_ctx* c) {
     return TFB_OK;
 }
 
+// the pose the scene was last updated with, as the device holds it (the host mirror is only refreshed by the frame path)
+static int current_pose_w2c(tfb_ctx* c, float out[16]) {
+    DevState ds;
+    TFB_CUDA(c, cudaMemcpy(&ds, c->ds, sizeof(ds), cudaMemcpyDeviceToHost));
+    memcpy(out, ds.pose_w2c, 16 * sizeof(float));
+    return TFB_OK;
+}
+
 static int stream_out_impl(tfb_ctx* c, int max_blocks, int* n_out) {
     int r = tfb_sync(c);
     if (r || (r = stream_prepare(c))) return r;
     HostBlockStore* st = c->store;
     const int N = HostBlockStore::CHUNK;
     int done = 0;
+    float pose[16];
+    if ((r = current_pose_w2c(c, pose))) return r;
     for (;;) {
         const int want = max_blocks > 0 ? (max_blocks - done < N ? max_blocks - done : N) : N;
         if (want <= 0) break;
-        if ((r = launch_stream_select(c, 0, c->hs->pose_w2c, st->list_dev, want, st->counter_dev))) return r;
+        if ((r = launch_stream_select(c, 0, pose, st->list_dev, want, st->counter_dev))) return r;
         TFB_CUDA(c, cudaMemcpyAsync(st->list_host + 2 * N, st->counter_dev, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         TFB_CUDA(c, cudaStreamSynchronize(c->stream));
         const int found = st->list_host[2 * N];
@@ -406,8 +416,11 @@ static int stream_in_impl(tfb_ctx* c, const float* pose_w2c, int all, int* n_in,
     const int N = HostBlockStore::CHUNK;
     int done = 0;
     bool pool_full = false;
+    float pose[16];
+    if (pose_w2c) memcpy(pose, pose_w2c, sizeof(pose));
+    else if ((r = current_pose_w2c(c, pose))) return r;
     while (!st->where.empty() && !pool_full) {
-        if ((r = launch_stream_select(c, all ? 2 : 1, pose_w2c ? pose_w2c : c->hs->pose_w2c, st->list_dev, N, st->counter_dev))) return r;
+        if ((r = launch_stream_select(c, all ? 2 : 1, pose, st->list_dev, N, st->counter_dev))) return r;
         TFB_CUDA(c, cudaMemcpyAsync(st->list_host + 2 * N, st->counter_dev, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         TFB_CUDA(c, cudaMemcpyAsync(st->list_host, st->list_dev, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         TFB_CUDA(c, cudaStreamSynchronize(c->stream));
