@@ -161,7 +161,12 @@ int do_preprocess(tfb_ctx* c, const uint16_t* depth_dev, bool maps_into_model) {
 }
 
 // ProjectiveICP::estimateTransform, projective_icp.cpp:169-212 — every iteration is one launch, nothing returns to the host
-int do_icp(tfb_ctx* c, bool update_pose) { return launch_icp_all(c, update_pose); }
+int do_icp(tfb_ctx* c, bool update_pose) {
+    c->icp_fuse_type3 = true;    // an allocation stage follows a tracked frame (or nothing does, when tracking fails)
+    const int r = launch_icp_all(c, update_pose);
+    c->icp_fuse_type3 = false;
+    return r;
+}
 
 constexpr int MARKS_CAP = 1 << 16;
 
@@ -241,6 +246,7 @@ int frame_end(tfb_ctx* c, int* ok) {
     }
     if (c->hs->icp_failed) {  // topfu.cpp:263-264: return reset(), false
         c->voxel_updates_last = 0;
+        c->type3_done = false;   // k_icp_all's epilogue did not run setToType3 either
         if ((r = do_reset(c))) return r;
         *ok = 0;
         return TFB_OK;
@@ -416,6 +422,7 @@ int do_frame(tfb_ctx* c, const uint16_t* depth, size_t host_step_bytes, int* ok,
     }
     if (c->hs->icp_failed) {  // topfu.cpp:263-264: return reset(), false
         c->voxel_updates_last = 0;
+        c->type3_done = false;   // k_icp_all's epilogue did not run setToType3 either
         if ((r = do_reset(c))) return r;
         *ok = 0;
         return TFB_OK;

@@ -155,6 +155,8 @@ struct tfb_ctx {
     unsigned int* claim_key;   // per slot, 0 = unclaimed
     int* claimed;              // compact list of claimed slots
     unsigned int* bucket_bits; // 1 bit per bucket: head entry allocated (empty-space skipping without touching the table)
+    bool icp_fuse_type3;       // set around the frame path's ICP launch: k_icp_all's epilogue does setToType3
+    bool type3_done;           // ... and the next launch_allocate skips k_set_type3
     struct HostBlockStore* store;   // blocks streamed out to the host (tfb_stream_out / tfb_stream_in), created on first use
     int2* block_dir;           // dense directory of the blocks around the origin, {slot, ptr} per block or {-1, -1}: see BlockDir
     // render state

@@ -551,7 +551,8 @@ __device__ __forceinline__ void icp_pixels(const IcpLevelArgs& L, const IcpAllAr
 }
 
 __global__ void __launch_bounds__(ICPA_THREADS, 1)
-    k_icp_all(IcpAllArgs a, DevState* __restrict__ ds, float* __restrict__ partial, unsigned int* host_state, unsigned int host_seq) {
+    k_icp_all(IcpAllArgs a, DevState* __restrict__ ds, float* __restrict__ partial, unsigned int* host_state, unsigned int host_seq,
+              int* __restrict__ vis, const int* list0, const int* list1) {
     __shared__ float s_warp[ICPA_WARPS][ICP_ACC];
     __shared__ double s_part[ICPA_WARPS][32];
     __shared__ double s_tot[ICP_ACC];
@@ -734,6 +735,16 @@ __global__ void __launch_bounds__(ICPA_THREADS, 1)
         }
     }
 
+    // setToType3 (SceneReconstructionEngine_host.cu:343-348) for the allocation stage that follows a tracked frame: every entry of
+    // the current visible list becomes "visible in the previous frame, to be re-tested".  It used to be the first launch of the
+    // frame's tail (k_set_type3: 3 us of kernel and a launch boundary on the critical path between this kernel and k_mark); here
+    // the 147 CTAs that have nothing left to do take it — at the same point of the stream order, under the same condition
+    // (skipped when tracking failed, as k_set_type3 is), so the allocation stage sees exactly what it saw before.
+    if (vis != nullptr && ok) {
+        const int* __restrict__ list = ds->cur_list ? list1 : list0;
+        const int n = ds->n_visible;
+        for (int i = blockIdx.x * ICPA_THREADS + tid; i < n; i += (int)gridDim.x * ICPA_THREADS) vis[list[i]] = 3;
+    }
     if (blockIdx.x != 0) return;
     if (tid == 0) {
         ds->icp_failed = ok ? 0 : 1;
@@ -758,16 +769,20 @@ __global__ void __launch_bounds__(ICPA_THREADS, 1)
     // The frame's result — pose, verdict, counters: the whole state block — goes straight into the host's pinned mirror
     // (zero-copy), followed by a sequence number the host spins on: no D2H copy to enqueue, no stream synchronise to wake
     // up from (the reference: 19 stream syncs + a blocking cudaMemcpy per frame just for ICP).
-    if (host_state == nullptr) return;
-    __syncthreads();
-    constexpr int WORDS = (int)(sizeof(DevState) / sizeof(unsigned int));
-    const unsigned int* src = reinterpret_cast<const unsigned int*>(ds);
-    for (int i = tid; i < WORDS; i += ICPA_THREADS) host_state[i] = src[i];
-    __syncthreads();
-    if (tid == 0) {
-        __threadfence_system();
-        *reinterpret_cast<volatile unsigned int*>(host_state + WORDS) = host_seq;
+    if (host_state != nullptr) {
+        __syncthreads();
+        constexpr int WORDS = (int)(sizeof(DevState) / sizeof(unsigned int));
+        const unsigned int* src = reinterpret_cast<const unsigned int*>(ds);
+        for (int i = tid; i < WORDS; i += ICPA_THREADS) host_state[i] = src[i];
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned int*>(host_state + WORDS) = host_seq;
+        }
     }
+    // the other half of k_set_type3: the allocation counters of the frame start from zero (after the snapshot above, which
+    // still reports the previous frame's)
+    if (vis != nullptr && ok && tid == 0) { ds->n_claimed = 0; ds->n_new_frame = 0; }
 }
 
 #ifdef TFB_ICP_PROFILE
@@ -847,7 +862,11 @@ static int launch_icp_args(tfb_ctx* c, IcpAllArgs& a, int total) {
     // the frame path asks for the zero-copy publish (c->publish_seq != 0); stage-level calls read the state back themselves
     unsigned int* host_state = c->publish_seq ? reinterpret_cast<unsigned int*>(c->hs) : nullptr;
     unsigned int host_seq = c->publish_seq;
-    void* args[] = {&a, &ds, &partial, &host_state, &host_seq};
+    // the frame path lets the kernel's idle CTAs do setToType3 for the allocation stage that follows (launch_allocate skips its own)
+    int* vis = c->icp_fuse_type3 ? c->vis_type : nullptr;
+    const int *l0 = c->vis_list[0], *l1 = c->vis_list[1];
+    if (vis) c->type3_done = true;
+    void* args[] = {&a, &ds, &partial, &host_state, &host_seq, &vis, &l0, &l1};
     TFB_KT(c, K_ICP_ALL);
     TFB_CUDA(c, cudaLaunchCooperativeKernel((const void*)k_icp_all, dim3(c->icp_grid), dim3(ICPA_THREADS), args, 0, c->stream));
     TFB_LAUNCH_CHECK(c);
