@@ -1012,13 +1012,30 @@ int tfb_timing_last_ms(tfb_ctx* c, float out9[9]) {
 }
 long long tfb_kernel_launches(const tfb_ctx* c) { return c ? c->launches : 0; }
 
-// write a buffer larger than the 126 MB L2 so the next step starts from HBM (bench timing hygiene)
+// write a buffer larger than the 126 MB L2 so the next step starts from HBM (bench timing hygiene).  TFB_FLUSH_READBACK=1 (tools
+// only): the first half of the scratch is then read back, so what the L2 holds afterwards are CLEAN scratch lines — the timed
+// kernel's misses evict them for free instead of paying the write-back of the flusher's dirty lines.
+__global__ void __launch_bounds__(256) k_l2_readback(const uint4* __restrict__ p, size_t n, unsigned int* sink) {
+    unsigned int acc = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 v = __ldcg(p + i);
+        acc ^= v.x ^ v.y ^ v.z ^ v.w;
+    }
+    if (acc == 0x12345678u) *sink = acc;   // never true for a memset pattern; keeps the loads
+}
+
 int tfb_flush_l2(tfb_ctx* c) {
     if (!c) return TFB_ERR_ARG;
     const size_t bytes = (size_t)256 << 20;
-    if (!c->l2_scratch) TFB_CUDA(c, cudaMalloc(&c->l2_scratch, bytes));
+    if (!c->l2_scratch) TFB_CUDA(c, cudaMalloc(&c->l2_scratch, bytes + 256));
     c->l2_toggle ^= 1;
     TFB_CUDA(c, cudaMemsetAsync(c->l2_scratch, c->l2_toggle, bytes, c->stream));
+    static const bool readback = getenv("TFB_FLUSH_READBACK") && atoi(getenv("TFB_FLUSH_READBACK")) != 0;
+    if (readback) {
+        k_l2_readback<<<NUM_SMS * 8, 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(c->l2_scratch), (bytes / 2) / sizeof(uint4),
+                                                         reinterpret_cast<unsigned int*>(static_cast<char*>(c->l2_scratch) + bytes));
+        TFB_LAUNCH_CHECK(c);
+    }
     return TFB_OK;
 }
 

@@ -133,7 +133,8 @@ __device__ __noinline__ void solve6_jacobi(const double* A, const double* b, dou
 struct Ldl6 {
     float l[6][6];
     float dinv[6];
-    double det;
+    float d[6];       // the pivots; their product is the determinant
+    float dmin;
     bool ok;
 };
 
@@ -144,7 +145,7 @@ __device__ __forceinline__ void ldl6_f32(const float (&A)[36], Ldl6& f) {
     const float tiny = amax * 4e-6f;
     float d[6];
     f.ok = true;
-    f.det = 1.0;
+    f.dmin = 3.0e38f;
     // this runs on ONE thread, 19 times per frame, on the critical path of every iteration: fused multiply-adds, the
     // products l[j][k] * d[k] shared by the column below, and a Newton-refined MUFU reciprocal instead of a division
 #pragma unroll
@@ -155,7 +156,8 @@ __device__ __forceinline__ void ldl6_f32(const float (&A)[36], Ldl6& f) {
         for (int k = 0; k < j; ++k) { ld[k] = f.l[j][k] * d[k]; dj = __fmaf_rn(-f.l[j][k], ld[k], dj); }
         if (!(dj > tiny)) f.ok = false;
         d[j] = dj;
-        f.det *= (double)dj;
+        f.d[j] = dj;
+        f.dmin = fminf(f.dmin, dj);
         float y0;
         asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(dj));
         f.dinv[j] = __fmaf_rn(y0, __fmaf_rn(-dj, y0, 1.0f), y0);
@@ -227,41 +229,14 @@ __device__ __noinline__ bool solve6_reference_path(const float* Af_, const float
     return true;
 }
 
-// StreamHelper::get unpack (projective_icp.cpp:43-62), nullspace test (:197-203), solve (:206),
-// Tinc = Affine3f(rvec, t) and affine = Tinc * affine (:208-209).  aff is the running estimate (row-major).
-// Returns false when tracking failed.
-__device__ __noinline__ bool icp_solve_update(const double* v27, float* aff_io) {
-    float aff[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) aff[i] = aff_io[i];
-    float Af[36], bf[6];
-    {
-        int shift = 0;
-#pragma unroll
-        for (int i = 0; i < 6; ++i)
-#pragma unroll
-            for (int j = i; j < 7; ++j) {
-                const float value = (float)v27[shift++];
-                if (j == 6) bf[i] = value;
-                else { Af[j * 6 + i] = value; Af[i * 6 + j] = value; }
-            }
-    }
-    float rf[6];
-    Ldl6 f;
-    ldl6_f32(Af, f);
-    bool solved = false;
-    if (f.ok && f.det == f.det && fabs(f.det) >= 1e-15) solved = solve6_refine(Af, bf, f, rf);
-    if (!solved) {
-        double r[6];
-        if (!solve6_reference_path(Af, bf, r)) return false;
-#pragma unroll
-        for (int i = 0; i < 6; ++i) rf[i] = (float)r[i];
-    }
-
+// Tinc = Affine3f(rvec, t) and affine = Tinc * affine (projective_icp.cpp:208-209); aff is the running estimate (row-major,
+// rows 0..2 — row 3 is (0, 0, 0, 1) from the identity the loop starts with and every product keeps it, so neither operand's
+// fourth row is multiplied out).
+__device__ __forceinline__ void icp_apply_increment(const float (&rf)[6], float* aff_io) {
     // cv::Affine3f(rvec, t) = Rodrigues: R = cos I + (1 - cos) r r^T + sin [r]x.  OpenCV evaluates it
     // in double and stores float; the increments here are fractions of a degree, where fp32 series for sin, cos and
     // (1 - cos) — the latter summed directly, without the cancellation of 1 - cos — are exact to the last float bit or two.
-    float T[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    float T[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
     const float t2 = rf[0] * rf[0] + rf[1] * rf[1] + rf[2] * rf[2];
     if (t2 > 0.f) {
         const float theta = sqrtf(t2);
@@ -281,10 +256,74 @@ __device__ __noinline__ bool icp_solve_update(const double* v27, float* aff_io) 
         T[8] = c1 * rx * rz - sn * ry; T[9] = c1 * ry * rz + sn * rx; T[10] = cs + c1 * rz * rz;
     }
     T[3] = rf[3]; T[7] = rf[4]; T[11] = rf[5];
-    float nw[16];
-    pose_mul(T, aff, nw);
+    float a[12], nw[12];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) aff_io[i] = nw[i];
+    for (int i = 0; i < 12; ++i) a[i] = aff_io[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float v = T[i * 4] * a[c];
+            v += T[i * 4 + 1] * a[4 + c];
+            v += T[i * 4 + 2] * a[8 + c];
+            if (c == 3) v += T[i * 4 + 3];
+            nw[i * 4 + c] = v;
+        }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) aff_io[i] = nw[i];
+}
+
+// StreamHelper::get unpack (projective_icp.cpp:43-62): the 27 sums -> symmetric A (6x6) and b
+__device__ __forceinline__ void icp_unpack(const float* v27, float (&Af)[36], float (&bf)[6]) {
+    int shift = 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = i; j < 7; ++j) {
+            const float value = v27[shift++];
+            if (j == 6) bf[i] = value;
+            else { Af[j * 6 + i] = value; Af[i * 6 + j] = value; }
+        }
+}
+
+// the system the fast path declined: the reference's nullspace test and least-norm solve, out of line (its arrays live in
+// local memory; the fast path's stay in registers because nothing takes their address)
+__device__ __noinline__ bool icp_solve_slow(const float* v27, float* aff_io) {
+    float Af[36], bf[6];
+    icp_unpack(v27, Af, bf);
+    double r[6];
+    if (!solve6_reference_path(Af, bf, r)) return false;
+    float rf[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) rf[i] = (float)r[i];
+    icp_apply_increment(rf, aff_io);
+    return true;
+}
+
+// Unpack, nullspace test (projective_icp.cpp:197-203), solve (:206), Tinc * affine (:208-209).  v27: the folded sums as fp32
+// (shared memory), aff_io: the running estimate, updated in place on success.  Returns false when tracking failed.
+// One thread, 19 times a frame, on the critical path of every iteration: straight-line register code.  The determinant of
+// the nullspace test is the product of the six pivots; when the smallest pivot is above (1e-15)^(1/6) = 3.17e-3 — always, for
+// sums over 10^5 pixels — the product need not be formed to know it passes (it was a chain of six fp64 multiplies).
+__device__ __forceinline__ bool icp_solve_update(const float* v27, float* aff_io) {
+    float Af[36], bf[6];
+    icp_unpack(v27, Af, bf);
+    float rf[6];
+    Ldl6 f;
+    ldl6_f32(Af, f);
+    bool solved = false;
+    if (f.ok) {
+        bool det_ok = f.dmin >= 3.2e-3f;
+        if (!det_ok) {
+            double det = 1.0;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) det *= (double)f.d[i];
+            det_ok = fabs(det) >= 1e-15;
+        }
+        if (det_ok) solved = solve6_refine(Af, bf, f, rf);
+    }
+    if (!solved) return icp_solve_slow(v27, aff_io);
+    icp_apply_increment(rf, aff_io);
     return true;
 }
 
@@ -405,7 +444,10 @@ __global__ void __launch_bounds__(ICP_THREADS)
             for (int i = 0; i < ICP_TERMS; ++i) out27[i] = (float)s_tot[i];
         if (solve) {
             float aff[16] = {r00, r01, r02, t0, r10, r11, r12, t1, r20, r21, r22, t2, 0.f, 0.f, 0.f, 1.f};
-            const bool ok = icp_solve_update(s_tot, aff);
+            float v27[ICP_TERMS];
+#pragma unroll
+            for (int i = 0; i < ICP_TERMS; ++i) v27[i] = (float)s_tot[i];
+            const bool ok = icp_solve_update(v27, aff);
             if (a.first_iter || !ok) ds->icp_failed = ok ? 0 : 1;
             if (ok) {
 #pragma unroll
@@ -556,7 +598,8 @@ __global__ void __launch_bounds__(ICPA_THREADS, 1)
     __shared__ float s_warp[ICPA_WARPS][ICP_ACC];
     __shared__ double s_part[ICPA_WARPS][32];
     __shared__ double s_tot[ICP_ACC];
-    __shared__ float s_aff[16];
+    __shared__ __align__(16) float s_totf[ICP_ACC];
+    __shared__ __align__(16) float s_aff[16];
     __shared__ int s_ok;
     __shared__ int s_list[ICP_LIST_SLOTS * ICPA_THREADS];       // the CTA's valid pixels of the current level
     __shared__ int s_cnt[ICP_LIST_SLOTS * ICPA_WARPS + 1];
@@ -714,21 +757,11 @@ __global__ void __launch_bounds__(ICPA_THREADS, 1)
 #pragma unroll
                 for (int p = 0; p < ICPA_WARPS; ++p) sd += s_part[p][tid];
                 s_tot[tid] = sd;
+                s_totf[tid] = (float)sd;   // StreamHelper::get hands the host floats: 28 conversions side by side, not 27 in the solving thread
             }
             __syncthreads();
             ICP_STAMP(4);
-            if (tid == 0) {
-                float aff[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) aff[i] = s_aff[i];
-                const bool good = icp_solve_update(s_tot, aff);
-                if (good) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) s_aff[i] = aff[i];
-                } else {
-                    s_ok = 0;
-                }
-            }
+            if (tid == 0 && !icp_solve_update(s_totf, s_aff)) s_ok = 0;   // s_aff is updated in place, and only on success
             ICP_STAMP(5);
             __syncthreads();
             ok = (s_ok != 0);
