@@ -61,7 +61,7 @@ void free_all(tfb_ctx* c) {
     stream_store_free(c);
     cudaFree(c->table); cudaFree(c->vba); cudaFree(c->vba_free); cudaFree(c->excess_free);
     cudaFree(c->claim_key); cudaFree(c->claimed); cudaFree(c->bucket_bits); cudaFree(c->block_dir); cudaFree(c->vis_type); cudaFree(c->vis_list[0]); cudaFree(c->vis_list[1]); cudaFree(c->cache_pool); cudaFree(c->cache_tag);
-    cudaFree(c->minmax); cudaFree(c->raycast); cudaFree(c->dists_buf[0]); cudaFree(c->dists_buf[1]); cudaFree(c->depth_in); cudaFree(c->icp_partial);
+    cudaFree(c->minmax); cudaFree(c->raycast); cudaFree(c->dists_buf[0]); cudaFree(c->dists_buf[1]); cudaFree(c->depth_in); cudaFree(c->icp_partial); cudaFree(c->icp_vlist); cudaFree(c->icp_vmask); cudaFree(c->icp_vscan);
     cudaFree(c->ds); cudaFree(c->l2_scratch); cudaFree(c->marks); cudaFree(c->shard_dev); cudaFree(c->sync_flags);
     for (int l = 0; l < MAX_LEVELS; ++l) {
         cudaFree(c->lv[l].depth); cudaFree(c->lv[l].vcurr); cudaFree(c->lv[l].ncurr); cudaFree(c->lv[l].vprev); cudaFree(c->lv[l].nprev);
@@ -140,11 +140,14 @@ inline void stamp(tfb_ctx* c, int i) {
 }
 
 // cuda::computeDists + depthBilateralFilter + depthTruncation + depthBuildPyramid + computePointNormals (topfu.cpp:166-197)
-int do_preprocess(tfb_ctx* c, const uint16_t* depth_dev, bool maps_into_model) {
+int do_preprocess(tfb_ctx* c, const uint16_t* depth_dev, bool maps_into_model, bool frame_path = false) {
     const tfb_params& p = c->p;
     int r = launch_bilateral(c, depth_dev, c->lv[0].depth, p.cols, p.rows, p.bilateral_kernel_size, p.bilateral_sigma_spatial,
                              p.bilateral_sigma_depth, p.icp_truncate_depth_dist, c->dists);
     if (r) return r;
+    // the frame path hands k_icp_all the level-0 pixels that hold a vertex as one ascending list (equal shares per CTA): the
+    // level-0 launch leaves a validity bit per pixel, the last launch compacts them in extra CTAs (tfb_imgproc.cu)
+    const bool with_list = frame_path && !maps_into_model && c->levels >= 2 && (p.cols % 32) == 0;
     for (int i = 0; i < c->levels; ++i) {
         int div = 1 << i;  // Intr::operator()(level), src/precomp.cpp:10-14
         // frame 0 ends with curr_.points_pyr.swap(prev_.points_pyr) (topfu.cpp:205-207): write the model maps directly
@@ -152,11 +155,13 @@ int do_preprocess(tfb_ctx* c, const uint16_t* depth_dev, bool maps_into_model) {
         float4* n = maps_into_model ? c->lv[i].nprev : c->lv[i].ncurr;
         if (i + 1 < c->levels)   // level i -> depth of level i+1 and maps of level i, one launch
             r = launch_pyr_maps(c, c->lv[i].depth, c->lv[i + 1].depth, v, n, c->lv[i].w, c->lv[i].h, p.bilateral_sigma_depth, p.fx / div,
-                                p.fy / div, p.cx / div, p.cy / div);
+                                p.fy / div, p.cx / div, p.cy / div, (with_list && i == 0) ? c->icp_vmask : nullptr);
         else
-            r = launch_points_normals(c, c->lv[i].depth, v, n, c->lv[i].w, c->lv[i].h, p.fx / div, p.fy / div, p.cx / div, p.cy / div);
+            r = launch_points_normals(c, c->lv[i].depth, v, n, c->lv[i].w, c->lv[i].h, p.fx / div, p.fy / div, p.cx / div, p.cy / div,
+                                      with_list);
         if (r) return r;
     }
+    c->vlist_ready = with_list;
     return TFB_OK;
 }
 
@@ -165,6 +170,7 @@ int do_icp(tfb_ctx* c, bool update_pose) {
     c->icp_fuse_type3 = true;    // an allocation stage follows a tracked frame (or nothing does, when tracking fails)
     const int r = launch_icp_all(c, update_pose);
     c->icp_fuse_type3 = false;
+    c->vlist_ready = false;
     return r;
 }
 
@@ -179,7 +185,7 @@ int frame_begin(tfb_ctx* c, const uint16_t* depth_dev) {
     stamp(c, ST_PRE);
     const bool first = (c->frame_counter == 0);
     c->frame_first = first;
-    if ((r = do_preprocess(c, depth_dev, first))) return r;
+    if ((r = do_preprocess(c, depth_dev, first, true))) return r;
     stamp(c, ST_ICP);
     if (!first && (r = do_icp(c, true))) return r;
     stamp(c, ST_ALLOC);
@@ -354,7 +360,7 @@ int do_frame(tfb_ctx* c, const uint16_t* depth, size_t host_step_bytes, int* ok,
             e = cudaMemcpy2DAsync(c->depth_in, row, depth, host_step_bytes, row, c->p.rows, cudaMemcpyHostToDevice, c->stream);
             src = c->depth_in;
         }
-        r = (e == cudaSuccess) ? do_preprocess(c, src, first) : set_err(c, TFB_ERR_CUDA, "frame upload", e);
+        r = (e == cudaSuccess) ? do_preprocess(c, src, first, true) : set_err(c, TFB_ERR_CUDA, "frame upload", e);
         if (c->timing) cudaEventRecord(c->ev_pre1, c->stream);
         if (r == TFB_OK && cudaEventRecord(c->ev_join, c->stream) != cudaSuccess) r = set_err(c, TFB_ERR_CUDA, "event record");
         c->stream = main_stream;
@@ -546,6 +552,9 @@ int tfb_create(const tfb_params* p, void* stream, tfb_ctx** out) {
     const size_t n_partial = (size_t)128 * (c->icp_max_blocks > 1024 ? c->icp_max_blocks : 1024) + 128;
     ok(dmalloc(&c->icp_partial, n_partial));
     if (e == cudaSuccess) cudaMemsetAsync(c->icp_partial, 0, n_partial * sizeof(float), c->stream);   // no stale epochs
+    ok(cudaMalloc((void**)&c->icp_vlist, (size_t)p->cols * p->rows * sizeof(int)));
+    ok(cudaMalloc((void**)&c->icp_vmask, ((size_t)p->cols * p->rows / 32 + 64) * sizeof(unsigned int)));
+    ok(cudaMalloc((void**)&c->icp_vscan, 8 * sizeof(unsigned int)));
     ok(cudaMalloc((void**)&c->ds, sizeof(DevState) + 64 * sizeof(float)));
     ok(cudaMalloc((void**)&c->marks, (size_t)(2 + 2 * MARKS_CAP) * sizeof(unsigned int)));
     ok(cudaMalloc((void**)&c->shard_dev, sizeof(ShardView)));

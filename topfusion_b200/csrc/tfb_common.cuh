@@ -174,6 +174,10 @@ struct tfb_ctx {
     int icp_max_blocks;
     int icp_grid;              // persistent ICP grid (co-resident CTAs), sized on first use
     unsigned int icp_launches; // epoch range of the partial rows, 64 per launch
+    int* icp_vlist;            // level-0 pixels that have a vertex, ascending (built inside the preprocessing launches, tfb_imgproc.cu)
+    unsigned int* icp_vmask;   // one validity bit per level-0 pixel (k_pyr_maps)
+    unsigned int* icp_vscan;   // [0] = length of the list
+    bool vlist_ready;          // the list belongs to the current maps of the frame path (consumed by the next k_icp_all)
     unsigned int publish_seq;  // != 0: k_icp_all writes the state block + this number into the pinned mirror (zero-copy)
     unsigned int seq_counter;
     // state
@@ -274,9 +278,9 @@ int launch_bilateral(tfb_ctx* c, const uint16_t* src, uint16_t* dst, int w, int 
 int launch_truncate(tfb_ctx* c, uint16_t* depth, int w, int h, float max_dist);
 int launch_depth_pyr(tfb_ctx* c, const uint16_t* src, uint16_t* dst, int sw, int sh, float sigma_depth_m);
 int launch_pyr_maps(tfb_ctx* c, const uint16_t* src, uint16_t* dst, float4* pts, float4* nrm, int sw, int sh, float sigma_depth_m,
-                    float fx, float fy, float cx, float cy);
+                    float fx, float fy, float cx, float cy, unsigned int* vmask = nullptr);
 int launch_points_normals(tfb_ctx* c, const uint16_t* depth, float4* pts, float4* nrm, int w, int h, float fx, float fy,
-                          float cx, float cy);
+                          float cx, float cy, bool with_valid_list = false);
 int launch_resize_points_normals(tfb_ctx* c, const float4* v, const float4* n, float4* vo, float4* no, int sw, int sh);
 // icp
 int launch_icp_iteration(tfb_ctx* c, int level, const float4* vcurr, const float4* ncurr, const float4* vprev,

@@ -485,6 +485,8 @@ struct IcpLevelArgs {
     const float4* nprev;
     int w, h, iters;
     float fx, fy, cx, cy;
+    const int* vlist;            // the level's pixels that have a vertex, ascending (tfb_imgproc.cu), or null: the CTA compacts its own slots
+    const unsigned int* vlist_n;
 };
 
 struct IcpAllArgs {
@@ -631,7 +633,22 @@ __global__ void __launch_bounds__(ICPA_THREADS, 1)
         // per thread, 10 times over.  The round-robin dealing of warps makes the lists of all CTAs equally long.
         const int slots = (npx + gstride - 1) / gstride;
         int n_list = -1;
-        if (slots <= ICP_LIST_SLOTS && L.iters > 0) {
+        // Level 0 of the frame path: the list of valid pixels exists already (built inside the preprocessing launches on the second
+        // stream, tfb_imgproc.cu), and every CTA takes an equal share of it.  Compacting its own slots, a CTA ends up with 896..1092 entries at
+        // 640x480 (the content is spatially coherent), and the dozen CTAs past 1024 entries — a third pixel per thread in one
+        // warp, 2.0 us against a median of 1.25 — set the length of every one of the ten level-0 iterations.
+        if (L.vlist != nullptr && L.iters > 0) {
+            const int n_total = (int)__ldcg(L.vlist_n);
+            const int share = (n_total + nblk - 1) / nblk;
+            if (share <= ICP_LIST_SLOTS * ICPA_THREADS) {
+                __syncthreads();   // the previous level's list is no longer read
+                const int begin = min((int)blockIdx.x * share, n_total);
+                n_list = min(share, n_total - begin);
+                for (int i = tid; i < n_list; i += ICPA_THREADS) s_list[i] = __ldcg(L.vlist + begin + i);
+                __syncthreads();
+            }
+        }
+        if (n_list < 0 && slots <= ICP_LIST_SLOTS && L.iters > 0) {
             __syncthreads();   // the previous level's list is no longer read
             int cnt = 0;
             for (int u = 0; u < slots; ++u) {
@@ -872,6 +889,7 @@ int launch_icp_all(tfb_ctx* c, bool update_pose) {
         a.lv[l].fx = p.fx / div; a.lv[l].fy = p.fy / div; a.lv[l].cx = p.cx / div; a.lv[l].cy = p.cy / div;
         total += p.icp_iters[l];
     }
+    if (c->vlist_ready) { a.lv[0].vlist = c->icp_vlist; a.lv[0].vlist_n = c->icp_vscan; }
     return launch_icp_args(c, a, total);
 }
 

@@ -156,9 +156,60 @@ int launch_depth_pyr(tfb_ctx* c, const uint16_t* src, uint16_t* dst, int sw, int
 // n = -normalize((v01 - v00) x (v10 - v00)); NaN x4 when any of the three depths is 0 or on the
 // last row / column.
 // ---------------------------------------------------------------------------------------------
+// The list of level-0 pixels that hold a vertex, ascending, for k_icp_all (tfb_icp.cu: every CTA takes an equal share).  The
+// level-0 launch of k_pyr_maps leaves one validity bit per pixel (a word per 32 pixels: 38 KB at 640x480); a tile of 64 words
+// is compacted by one CTA, which finds its place in the list by counting the bits of all the words in front of its own —
+// no ticket, no look-back, no waiting between CTAs, a fixed order.  The tiles ride in the rows of k_points_normals' grid past
+// the image (the last launch of the preprocessing), so the list costs no launch and no event of its own.
+struct ValidListArgs {
+    const unsigned int* mask;   // null: no list
+    int n_words;
+    int* list;
+    unsigned int* n_total;
+    int image_rows;             // grid rows of the launch that belong to the image
+};
+constexpr int VL_WORDS = 64;    // words of 32 pixels per tile
+
+__device__ __forceinline__ void valid_list_tile(const ValidListArgs& a, int tile, int tid) {
+    __shared__ int s_w[8];
+    __shared__ int s_off[VL_WORDS + 1];
+    const int lane = tid & 31, warp = tid >> 5;
+    const int w0 = tile * VL_WORDS;
+    int before = 0;
+    for (int i = tid; i < w0; i += 256) before += __popc(__ldg(a.mask + i));
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+    if (lane == 0) s_w[warp] = before;
+    unsigned int mine = 0;
+    if (tid < VL_WORDS) {
+        mine = (w0 + tid < a.n_words) ? __ldg(a.mask + w0 + tid) : 0u;
+        s_off[tid] = __popc(mine);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) run += s_w[w];
+        for (int i = 0; i < VL_WORDS; ++i) { const int c = s_off[i]; s_off[i] = run; run += c; }
+        s_off[VL_WORDS] = run;
+        if (w0 + VL_WORDS >= a.n_words) *a.n_total = (unsigned int)run;   // the last tile knows the length
+    }
+    __syncthreads();
+    for (int k = warp; k < VL_WORDS; k += 8) {
+        if (w0 + k >= a.n_words) break;
+        const unsigned int m = __ldg(a.mask + w0 + k);
+        if ((m >> lane) & 1u) a.list[s_off[k] + __popc(m & ((1u << lane) - 1u))] = (w0 + k) * 32 + lane;
+    }
+}
+
 __global__ void __launch_bounds__(256) k_points_normals(const uint16_t* __restrict__ depth, float4* __restrict__ points,
                                                         float4* __restrict__ normals, int w, int h, float finvx, float finvy,
-                                                        float cx, float cy) {
+                                                        float cx, float cy, ValidListArgs vl) {
+    if (vl.mask != nullptr && (int)blockIdx.y >= vl.image_rows) {
+        const int tile = ((int)blockIdx.y - vl.image_rows) * (int)gridDim.x + (int)blockIdx.x;
+        if (tile * VL_WORDS < vl.n_words) valid_list_tile(vl, tile, threadIdx.y * 32 + threadIdx.x);
+        return;
+    }
     const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
     if (x >= w || y >= h) return;
     const float qnan = __int_as_float(0x7fffffff);
@@ -188,7 +239,7 @@ __global__ void __launch_bounds__(256) k_points_normals(const uint16_t* __restri
 // level l (points_normals_kernel, imgproc.cu:214-243) — the reference reads level l twice, in two kernels.
 __global__ void __launch_bounds__(PY_TX* PY_TY)
     k_pyr_maps(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, float4* __restrict__ points, float4* __restrict__ normals,
-               int sw, int sh, int dw, int dh, float thr, float finvx, float finvy, float cx, float cy) {
+               int sw, int sh, int dw, int dh, float thr, float finvx, float finvy, float cx, float cy, unsigned int* __restrict__ vmask) {
     constexpr int TW = 2 * PY_TX + 4, TH = 2 * PY_TY + 4;
     __shared__ uint16_t tile[TH][TW];
     const int x0 = 2 * blockIdx.x * PY_TX - 2, y0 = 2 * blockIdx.y * PY_TY - 2;
@@ -222,9 +273,10 @@ __global__ void __launch_bounds__(PY_TX* PY_TY)
         const int i = tid + k * PY_TX * PY_TY;
         const int lx = i & (2 * PY_TX - 1), ly = i / (2 * PY_TX);
         const int x = 2 * blockIdx.x * PY_TX + lx, y = 2 * blockIdx.y * PY_TY + ly;
-        if (x >= sw || y >= sh) continue;
+        const bool in = x < sw && y < sh;
         float4 p = make_float4(qnan, qnan, qnan, qnan), n = p;
-        if (x < sw - 1 && y < sh - 1) {
+        bool has_vertex = false;
+        if (in && x < sw - 1 && y < sh - 1) {
             float z00 = tile[ly + 2][lx + 2] * 0.001f;
             float z01 = tile[ly + 2][lx + 3] * 0.001f;
             float z10 = tile[ly + 3][lx + 2] * 0.001f;
@@ -238,29 +290,42 @@ __global__ void __launch_bounds__(PY_TX* PY_TY)
                 float r = 1.0f / sqrtf(__fmaf_rn(cr.x, cr.x, __fmaf_rn(cr.y, cr.y, cr.z * cr.z)));  // reference: rsqrt (approximate)
                 n = make_float4(-(cr.x * r), -(cr.y * r), -(cr.z * r), 1.0f);
                 p = make_float4(v00.x, v00.y, v00.z, 1.0f);
+                has_vertex = true;
             }
         }
-        points[y * sw + x] = p;
-        normals[y * sw + x] = n;
+        if (in) {
+            points[y * sw + x] = p;
+            normals[y * sw + x] = n;
+        }
+        if (vmask != nullptr) {   // a warp holds 32 consecutive pixels of one row, starting at a multiple of 32 (sw % 32 == 0)
+            const unsigned int m = __ballot_sync(0xffffffffu, has_vertex);
+            if ((threadIdx.x & 31) == 0 && in) vmask[(y * sw + x) >> 5] = m;
+        }
     }
 }
 
 int launch_pyr_maps(tfb_ctx* c, const uint16_t* src, uint16_t* dst, float4* pts, float4* nrm, int sw, int sh, float sigma_depth_m,
-                    float fx, float fy, float cx, float cy) {
+                    float fx, float fy, float cx, float cy, unsigned int* vmask) {
     float thr = sigma_depth_m * 1000 * 3;  // imgproc.cu:132,138
     int dw = sw / 2, dh = sh / 2;
     dim3 block(PY_TX, PY_TY), grid(div_up(sw, 2 * PY_TX), div_up(sh, 2 * PY_TY));
     TFB_KT(c, K_PYR_MAPS);
-    k_pyr_maps<<<grid, block, 0, c->stream>>>(src, dst, pts, nrm, sw, sh, dw, dh, thr, 1.f / fx, 1.f / fy, cx, cy);
+    k_pyr_maps<<<grid, block, 0, c->stream>>>(src, dst, pts, nrm, sw, sh, dw, dh, thr, 1.f / fx, 1.f / fy, cx, cy, vmask);
     TFB_LAUNCH_CHECK(c);
     return TFB_OK;
 }
 
 int launch_points_normals(tfb_ctx* c, const uint16_t* depth, float4* pts, float4* nrm, int w, int h, float fx, float fy, float cx,
-                          float cy) {
+                          float cy, bool with_valid_list) {
     dim3 block(32, 8), grid(div_up(w, 32), div_up(h, 8));
+    ValidListArgs vl;
+    vl.mask = nullptr; vl.n_words = 0; vl.list = nullptr; vl.n_total = nullptr; vl.image_rows = (int)grid.y;
+    if (with_valid_list) {   // the level-0 mask was written by the first k_pyr_maps of this preprocessing (same stream)
+        vl.mask = c->icp_vmask; vl.n_words = c->lv[0].w * c->lv[0].h / 32; vl.list = c->icp_vlist; vl.n_total = c->icp_vscan;
+        grid.y += div_up(div_up(vl.n_words, VL_WORDS), (int)grid.x);
+    }
     TFB_KT(c, K_POINTS_NORMALS);
-    k_points_normals<<<grid, block, 0, c->stream>>>(depth, pts, nrm, w, h, 1.f / fx, 1.f / fy, cx, cy);
+    k_points_normals<<<grid, block, 0, c->stream>>>(depth, pts, nrm, w, h, 1.f / fx, 1.f / fy, cx, cy, vl);
     TFB_LAUNCH_CHECK(c);
     return TFB_OK;
 }
