@@ -34,10 +34,11 @@ static bool read_pgm16(const std::string& path, std::vector<unsigned short>& px,
 }
 
 struct TopFuApp {
-    TopFuApp(bool corrected) {
+    TopFuApp(bool corrected, bool eager_tail) {
         TopFuParams params = TopFuParams::default_params();
         TopFuSceneConfig sc;
         sc.corrected_mode = corrected;
+        sc.eager_tail = eager_tail;   // --ring: host frames, nothing between two calls waits for the device
         topfu_ = TopFu::Ptr(new TopFu(params, sc));
     }
 
@@ -134,7 +135,7 @@ int main(int argc, char* argv[]) {
 
     OpenNISource capture;  // kept for call-sequence parity with demo.cpp; frames come from files
     (void)capture;
-    TopFuApp app(corrected);
+    TopFuApp app(corrected, use_ring);
     bool ok = use_ring ? app.execute_ring(argv[1], n) : app.execute(argv[1], n);
     if (!out.empty()) app.save_view(out);
     if (ok) app.take_cloud();

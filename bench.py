@@ -279,8 +279,9 @@ def ingest_leg(frames, mode, n_warm=10):
             out["synchronous"] = (n - n_warm) / (time.perf_counter() - t0)
             ctx.close()
             dev.free()
-            # (b) the ring
-            ctx = capi.Context(corrected_mode=mode)
+            # (b) the ring; nothing synchronises with the device between frames here, so the tail of a frame is enqueued
+            # behind its ICP (defer_tail = 2) and runs while the host fetches the next slot
+            ctx = capi.Context(corrected_mode=mode, defer_tail=2)
             decoders, slots = 2, 6
             ring = L.tfio_ring_open(d.encode(), slots, 0, n, 0, decoders)
             if not ring:

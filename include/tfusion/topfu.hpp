@@ -66,6 +66,9 @@ struct KF_EXPORTS TopFuSceneConfig {
     bool print_pose = false;      // the reference prints the pose every frame (topfu.cpp:252)
     bool defer_tail = true;       // operator() returns once the pose is known; integration / raycast of that frame run beside the
                                   // next frame's preprocessing (or before anything looks at the scene).  Results are identical.
+    bool eager_tail = false;      // with defer_tail: those stages are enqueued behind the frame's ICP in the same call (which still
+                                  // returns when the pose is known) — the GPU runs them while the host fetches the next frame.
+                                  // For loops that hand over host frames and do not look at the scene in between (io::FrameRing).
     bool ieee_arith = false;      // TSDF integration: false = the arithmetic of the reference's GPU build (bit-identical voxels to the
                                   // reference on the same GPU); true = IEEE, bit-identical to a host compile of the same function
 };

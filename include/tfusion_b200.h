@@ -65,7 +65,10 @@ typedef struct tfb_params {
     int32_t defer_tail;             /* 1 (default): tfb_process_frame returns as soon as the pose is known; allocation,
                                      * integration, raycast and model maps of that frame are enqueued by the next call (beside
                                      * its preprocessing, on a second stream) or by any call that looks at the scene.  0: the
-                                     * whole frame is finished before the call returns.  Results are identical. */
+                                     * whole frame is finished before the call returns.  2: the call still returns as soon as
+                                     * the pose is known, but those stages are already enqueued behind the frame's ICP — the GPU
+                                     * runs them while the host turns around (for consumers that do not synchronise with the
+                                     * device between frames: a decode-ahead ring, a script).  Results are identical. */
     int32_t ieee_arith;             /* TSDF integration arithmetic.  0 (default): the arithmetic of the reference's own GPU
                                      * build (tfusion/CMakeLists.txt:1: --ftz=true --prec-div=false, fused multiply-adds) —
                                      * every voxel bit-identical to what the reference's integrateIntoScene_device writes on

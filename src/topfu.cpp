@@ -74,7 +74,7 @@ void TopFu::create(const TopFuSceneConfig& sc) {
     p.num_blocks = sc.num_blocks; p.num_buckets = sc.num_buckets; p.excess_size = sc.excess_size;
     p.depth_cutoff_mm = sc.depth_cutoff_mm; p.corrected_mode = sc.corrected_mode ? 1 : 0;
     p.shard_rank = sc.shard_rank; p.shard_count = sc.shard_count;
-    p.defer_tail = sc.defer_tail ? 1 : 0;
+    p.defer_tail = sc.defer_tail ? (sc.eager_tail ? 2 : 1) : 0;
     p.ieee_arith = sc.ieee_arith ? 1 : 0;
     int rc = tfb_create(&p, 0, &ctx_);
     if (rc != TFB_OK) cuda::error("tfb_create failed (no CUDA device, or out of memory)", __FILE__, __LINE__, "TopFu::TopFu");

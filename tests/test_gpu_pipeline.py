@@ -134,12 +134,14 @@ def test_corrected_mode_tracks_the_orbit(gpu, s1_frames):
         g.close(); o.close()
 
 
-def test_reset_after_tracking_loss(gpu, s1_frames):
-    """a blank frame kills every correspondence -> operator() returns false and resets (topfu.cpp:263-264)"""
+@pytest.mark.parametrize("tail_mode", [1, 2])
+def test_reset_after_tracking_loss(gpu, s1_frames, tail_mode):
+    """a blank frame kills every correspondence -> operator() returns false and resets (topfu.cpp:263-264); with the tail
+    enqueued ahead of the verdict (defer_tail=2) its kernels must leave the scene alone"""
     from oracle import tfo
     depth, _, _ = s1_frames
     o = tfo.Oracle()
-    g = gpu.Context(ieee_arith=1)
+    g = gpu.Context(ieee_arith=1, defer_tail=tail_mode)
     try:
         blank = np.zeros_like(depth[0])
         seq = [depth[0], depth[1], blank, depth[2], depth[3]]
@@ -225,11 +227,13 @@ def test_against_committed_golden_vectors(gpu):
             g.close()
 
 
-def test_deferred_tail_is_result_identical(gpu, s1_frames):
+@pytest.mark.parametrize("tail_mode", [1, 2])
+def test_deferred_tail_is_result_identical(gpu, s1_frames, tail_mode):
     """defer_tail=1 (default): a call returns once the pose is known and the next call (or any look at the scene) runs
-    allocation .. model maps of that frame beside its own preprocessing.  Same bits as the strictly sequential frame."""
+    allocation .. model maps of that frame beside its own preprocessing.  defer_tail=2: they are enqueued behind the frame's
+    ICP in the same call, which still returns when the pose is known.  Same bits as the strictly sequential frame."""
     depth, _, _ = s1_frames
-    a = gpu.Context(corrected_mode=1, defer_tail=1)
+    a = gpu.Context(corrected_mode=1, defer_tail=tail_mode)
     b = gpu.Context(corrected_mode=1, defer_tail=0)
     try:
         for i in range(8):

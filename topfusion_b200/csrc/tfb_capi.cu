@@ -306,8 +306,9 @@ int enqueue_tail(tfb_ctx* c) {
 
 // every entry point that looks at (or changes) the scene, the lists or the model maps calls this first
 int settle(tfb_ctx* c) {
-    if (!c->tail_pending) return TFB_OK;
-    int r = enqueue_tail(c);
+    if (!c->tail_pending && !c->tail_inflight) return TFB_OK;
+    int r = c->tail_pending ? enqueue_tail(c) : TFB_OK;   // in flight (defer_tail = 2): already behind its frame's ICP
+    c->tail_inflight = false;
     if (r) return r;
     if ((r = fetch_state(c))) return r;   // counters and voxel-update count of the frame that has just been finished
     c->voxel_updates_last = (long long)c->hs->voxel_updates;
@@ -327,14 +328,23 @@ int do_frame(tfb_ctx* c, const uint16_t* depth, size_t host_step_bytes, int* ok,
     int r;
     const bool first = (c->frame_counter == 0);
     stamp(c, ST_UPLOAD);
-    // the second stream starts where the caller's work on the main stream ends
-    TFB_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));
-    TFB_CUDA(c, cudaStreamWaitEvent(c->stream_pre, c->ev_fork, 0));
-    const bool had_tail = c->tail_pending;
+    // defer_tail = 2 ("eager"): the tail of a frame is enqueued right behind its ICP, in the same call, and the call still
+    // returns when the pose is known — the GPU goes from the ICP straight into the tail while the host turns around (return,
+    // next frame, call, upload, preprocessing): for consumers that do not synchronise between frames
+    const bool eager = c->p.defer_tail == 2 && !collective;
+    const bool had_tail = c->tail_pending || c->tail_inflight;
+    // the second stream starts where the caller's work on the main stream ends — unless that work is the tail this context
+    // put there itself and the frame comes from host memory (uploaded below, on the second stream): the preprocessing shares
+    // no buffer with a tail in flight (metres image double-buffered, current maps last read by an ICP that has returned)
+    if (!(eager && c->tail_inflight && host_step_bytes)) {
+        TFB_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));
+        TFB_CUDA(c, cudaStreamWaitEvent(c->stream_pre, c->ev_fork, 0));
+    }
+    c->tail_inflight = false;
     // this frame's metres image must not overwrite the one the tail is still reading
     float* dists = (c->tail_dists == c->dists_buf[0]) ? c->dists_buf[1] : c->dists_buf[0];
     auto tail = [&]() -> int {
-        if (had_tail) return enqueue_tail(c);
+        if (c->tail_pending) return enqueue_tail(c);
         stamp(c, ST_ALLOC); stamp(c, ST_INTEG); stamp(c, ST_EXPECT); stamp(c, ST_RAYCAST); stamp(c, ST_PYR);
         return TFB_OK;
     };
@@ -386,6 +396,11 @@ int do_frame(tfb_ctx* c, const uint16_t* depth, size_t host_step_bytes, int* ok,
         c->publish_seq = 0u;
         if (r) return r;
         stamp(c, ST_FRAME);
+        if (eager) {   // every kernel of the tail returns at once when the tracking it follows has failed (ds->icp_failed)
+            c->tail_dists = dists;
+            if ((r = enqueue_tail(c))) return r;
+            c->tail_inflight = true;
+        }
         if (zero_copy) {
             volatile unsigned int* seq = reinterpret_cast<volatile unsigned int*>(c->hs) + sizeof(DevState) / sizeof(unsigned int);
             unsigned int spins = 0;
@@ -429,6 +444,7 @@ int do_frame(tfb_ctx* c, const uint16_t* depth, size_t host_step_bytes, int* ok,
     if (c->hs->icp_failed) {  // topfu.cpp:263-264: return reset(), false
         c->voxel_updates_last = 0;
         c->type3_done = false;   // k_icp_all's epilogue did not run setToType3 either
+        c->tail_inflight = false;
         if ((r = do_reset(c))) return r;
         *ok = 0;
         return TFB_OK;
@@ -436,6 +452,7 @@ int do_frame(tfb_ctx* c, const uint16_t* depth, size_t host_step_bytes, int* ok,
     if ((r = push_pose(c, c->hs->pose_c2w))) return r;
     c->frame_counter++;
     *ok = 1;
+    if (eager) return TFB_OK;   // the tail is already behind this frame's ICP
     c->tail_pending = true;
     c->tail_dists = dists;
     if (!c->p.defer_tail) return settle(c);

@@ -227,6 +227,7 @@ struct tfb_ctx {
     cudaStream_t stream_pre;
     cudaEvent_t ev_fork, ev_join, ev_pre0, ev_pre1, ev_alloc, ev_expect;
     bool tail_pending;         // allocation .. model maps of the last tracked frame are still to be enqueued
+    bool tail_inflight;        // defer_tail = 2: they were enqueued behind that frame's ICP and its counters have not been read yet
     const float* tail_dists;
 };
 
