@@ -176,7 +176,11 @@ __device__ __forceinline__ void valid_list_tile(const ValidListArgs& a, int tile
     const int lane = tid & 31, warp = tid >> 5;
     const int w0 = tile * VL_WORDS;
     int before = 0;
-    for (int i = tid; i < w0; i += 256) before += __popc(__ldg(a.mask + i));
+    const uint4* m4 = reinterpret_cast<const uint4*>(a.mask);   // w0 is a multiple of 64 words: whole 16-byte groups
+    for (int i = tid; i < w0 / 4; i += 256) {
+        const uint4 q = __ldg(m4 + i);
+        before += __popc(q.x) + __popc(q.y) + __popc(q.z) + __popc(q.w);
+    }
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
     if (lane == 0) s_w[warp] = before;
