@@ -281,6 +281,10 @@ TFB_API int tfb_export_dists(tfb_ctx* c, float* host);
 /* which: 0 current depth (u16), 1 current points, 2 current normals, 3 model points, 4 model normals */
 TFB_API int tfb_export_level(tfb_ctx* c, int which, int level, void* host);
 TFB_API int tfb_import_level(tfb_ctx* c, int which, int level, const void* host);
+/* the level-0 pixels that hold a vertex, ascending (row-major index), as the last tfb_process_frame left them for its ICP:
+ * proj_icp.cu:86-88 skips a pixel whose vertex is NaN; here every CTA of the ICP kernel takes an equal share of this list.
+ * *n = 0 before the first tracked frame, or when the image width is not a multiple of 32 (the list is then not built). */
+TFB_API int tfb_export_icp_valid_list(tfb_ctx* c, int32_t* host, int capacity, int* n);
 /* device pointers of the context's own buffers (same `which` codes; 5 = dists) */
 TFB_API void* tfb_level_ptr(tfb_ctx* c, int which, int level);
 

@@ -129,3 +129,24 @@ def test_icp_parameter_ranges_are_validated(gpu):
         gpu.Context(mu=0.5, voxel_size=0.002)
     c = gpu.Context(icp_iters=(30, 20, 13, 0))     # 63 in total: accepted
     c.close()
+
+
+def test_frame_path_valid_pixel_list(gpu, s1_frames):
+    """Level 0 of the frame path's ICP walks ONE ascending list of the pixels that hold a vertex (find_coresp skips a NaN vertex,
+    proj_icp.cu:86-88), of which every CTA takes an equal share: validity bits from the level-0 map kernel, compacted by extra
+    CTAs of the last preprocessing launch.  The list must be exactly the non-NaN vertices of the current level-0 map, in
+    pixel order, frame after frame — and the poses of that path must be reproducible to the bit."""
+    depth, _, _ = s1_frames
+    a, b = gpu.Context(corrected_mode=1), gpu.Context(corrected_mode=1)
+    try:
+        assert a.icp_valid_list().size == 0          # nothing tracked yet
+        for i in range(5):
+            assert a.process_frame(depth[i]) and b.process_frame(depth[i])
+            if i == 0:
+                continue                              # frame 0 writes its maps straight into the model pyramid, no ICP
+            want = np.flatnonzero(~np.isnan(a.level(1, 0)[..., 0].ravel())).astype(np.int32)
+            got = a.icp_valid_list()
+            assert got.size == want.size > 100000 and np.array_equal(got, want), i
+            assert np.array_equal(a.pose().view(np.uint32), b.pose().view(np.uint32)), i
+    finally:
+        a.close(); b.close()

@@ -520,6 +520,13 @@ class Context:
         a = np.ascontiguousarray(arr, dtype=np.uint16 if which == 0 else np.float32)
         self._ck(self.L.tfb_import_level(self.h, C.c_int(which), C.c_int(level), _np_ptr(a)))
 
+    def icp_valid_list(self) -> np.ndarray:
+        """level-0 pixels that hold a vertex, ascending, as the last tracked frame's ICP shared them out"""
+        out = np.empty(self.cols * self.rows, np.int32)
+        n = C.c_int(0)
+        self._ck(self.L.tfb_export_icp_valid_list(self.h, _np_ptr(out), C.c_int(out.size), C.byref(n)))
+        return out[:n.value].copy()
+
     def level_ptr(self, which: int, level: int) -> int:
         return int(self.L.tfb_level_ptr(self.h, C.c_int(which), C.c_int(level)))
 

@@ -162,6 +162,7 @@ int do_preprocess(tfb_ctx* c, const uint16_t* depth_dev, bool maps_into_model, b
         if (r) return r;
     }
     c->vlist_ready = with_list;
+    if (with_list) c->vlist_built = true;
     return TFB_OK;
 }
 
@@ -1015,6 +1016,18 @@ int tfb_export_level(tfb_ctx* c, int which, int level, void* host) {
     void* p = tfb_level_ptr(c, which, level);
     if (!p || !host) return TFB_ERR_ARG;
     return tfb_d2h(c, host, p, level_bytes(c, which, level));
+}
+int tfb_export_icp_valid_list(tfb_ctx* c, int32_t* host, int capacity, int* n) {
+    if (!c || !host || !n || capacity < 0) return TFB_ERR_ARG;
+    *n = 0;
+    if (!c->vlist_built) return TFB_OK;
+    unsigned int count = 0;
+    int r = tfb_d2h(c, &count, c->icp_vscan, sizeof(count));
+    if (r) return r;
+    if ((long long)count > (long long)c->p.cols * c->p.rows) return set_err(c, TFB_ERR_STATE, "valid-pixel list: implausible length");
+    *n = (int)count;
+    if ((int)count > capacity) return set_err(c, TFB_ERR_ARG, "valid-pixel list: capacity too small");
+    return count ? tfb_d2h(c, host, c->icp_vlist, (size_t)count * sizeof(int32_t)) : TFB_OK;
 }
 int tfb_import_level(tfb_ctx* c, int which, int level, const void* host) {
     if (c) TFB_SETTLE(c);

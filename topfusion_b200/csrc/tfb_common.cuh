@@ -177,6 +177,7 @@ struct tfb_ctx {
     int* icp_vlist;            // level-0 pixels that have a vertex, ascending (built inside the preprocessing launches, tfb_imgproc.cu)
     unsigned int* icp_vmask;   // one validity bit per level-0 pixel (k_pyr_maps)
     unsigned int* icp_vscan;   // [0] = length of the list
+    bool vlist_built;          // at least one list has been built (tfb_export_icp_valid_list)
     bool vlist_ready;          // the list belongs to the current maps of the frame path (consumed by the next k_icp_all)
     unsigned int publish_seq;  // != 0: k_icp_all writes the state block + this number into the pinned mirror (zero-copy)
     unsigned int seq_counter;
