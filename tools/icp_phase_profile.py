@@ -16,6 +16,14 @@ print("iter  pixels  reduce  barrier  fold  solve   | total(us)")
 for i in range(19):
     print("%3d  %6.2f  %6.2f  %6.2f  %6.2f  %6.2f   | %6.2f" % (i, *d[i], (t[i, 5] - t[i, 0]) / 1.965e3))
 print("sum of iterations: %.1f us; span first..last %.1f us" % (d.sum(), (t[18, 5] - t[0, 0]) / 1.965e3))
+g = out.reshape(64, 8)[60, :4].astype(np.float64)
+if g[0] > 0:
+    print("CTA 0, globaltimer: kernel entry -> first iteration %.2f us; first -> end of last iteration %.2f us; epilogue (type 3, pose, host publish) %.2f us"
+          % ((g[1] - g[0]) / 1e3, (g[2] - g[1]) / 1e3, (g[3] - g[2]) / 1e3))
+e = out.reshape(64, 8)[61, :4].astype(np.float64)
+if e[0] > 0:
+    print("epilogue of CTA 0 (clock64): result + pose matrices %.2f us, state block -> pinned host %.2f us, system fence + sequence word %.2f us"
+          % ((e[1] - e[0]) / 1.965e3, (e[2] - e[1]) / 1.965e3, (e[3] - e[2]) / 1.965e3))
 cta = np.zeros(1024, np.int64)
 if ctx.L.tfb_debug_icp_cta(cta.ctypes.data_as(C.c_void_p)) == 0:
     t = cta.reshape(256, 4)[:148].astype(np.float64)

@@ -621,6 +621,7 @@ __global__ void __launch_bounds__(ICPA_THREADS, 1)
     int iter_global = 0;
     bool ok = true;
 #ifdef TFB_ICP_PROFILE
+    if (blockIdx.x == 0 && tid == 0) { long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); g_icp_prof[60 * 8] = gt; }
     long long pix_t0 = 0;
     if (tid == 0 && blockIdx.x < 256) { unsigned int smid; asm("mov.u32 %0, %%smid;" : "=r"(smid)); g_icp_pix[blockIdx.x * 24] = (int)smid; }
 #endif
@@ -681,6 +682,9 @@ __global__ void __launch_bounds__(ICPA_THREADS, 1)
 #pragma unroll
             for (int i = 0; i < ICP_ACC; ++i) acc[i] = 0.f;
             ICP_STAMP(0);
+#ifdef TFB_ICP_PROFILE
+            if (iter_global == 0 && blockIdx.x == 0 && tid == 0) { long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); g_icp_prof[60 * 8 + 1] = gt; }
+#endif
 
             // pixels in flight per thread sized to the level: 5 at 640x480 (4.05 pixels per thread), 2 and 1 on the coarse levels
             if (n_list >= 0) {
@@ -790,49 +794,67 @@ __global__ void __launch_bounds__(ICPA_THREADS, 1)
     // frame's tail (k_set_type3: 3 us of kernel and a launch boundary on the critical path between this kernel and k_mark); here
     // the 147 CTAs that have nothing left to do take it — at the same point of the stream order, under the same condition
     // (skipped when tracking failed, as k_set_type3 is), so the allocation stage sees exactly what it saw before.
+#ifdef TFB_ICP_PROFILE
+    if (blockIdx.x == 0 && tid == 0) { long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); g_icp_prof[60 * 8 + 2] = gt; }
+#endif
     if (vis != nullptr && ok) {
-        const int* __restrict__ list = ds->cur_list ? list1 : list0;
-        const int n = ds->n_visible;
-        for (int i = blockIdx.x * ICPA_THREADS + tid; i < n; i += (int)gridDim.x * ICPA_THREADS) vis[list[i]] = 3;
+        // CTA 0 has the frame's result to compose and publish (below): the others share the list among themselves
+        const int workers = gridDim.x > 1 ? (int)gridDim.x - 1 : 1, me = gridDim.x > 1 ? (int)blockIdx.x - 1 : 0;
+        if (me >= 0) {
+            const int* __restrict__ list = ds->cur_list ? list1 : list0;
+            const int n = ds->n_visible;
+            for (int i = me * ICPA_THREADS + tid; i < n; i += workers * ICPA_THREADS) vis[list[i]] = 3;
+        }
     }
     if (blockIdx.x != 0) return;
-    if (tid == 0) {
-        ds->icp_failed = ok ? 0 : 1;
-        ds->icp_corresp = (int)s_tot[ICP_TERMS];
+#ifdef TFB_ICP_PROFILE
+    if (tid == 0) g_icp_prof[61 * 8] = clock64();
+#endif
+    if (warp == 0) {   // the first warp composes the frame's pose: the fp64 inverse spread over its lanes (tfb_pose.cuh)
+        if (lane == 0) {
+            ds->icp_failed = ok ? 0 : 1;
+            ds->icp_corresp = (int)s_tot[ICP_TERMS];
+        }
         // ds->affine: the running product — on failure the product of the iterations before the failing one, which is what
         // ProjectiveICP::estimateTransform leaves in its `affine` argument when it returns false (projective_icp.cpp:197-203)
+        if (lane < 16) ds->affine[lane] = s_aff[lane];
+        if (ok && a.update_pose) {
+            float aff[16], prev[16], nw[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) ds->affine[i] = s_aff[i];
-        if (ok) {
-            float aff[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) aff[i] = s_aff[i];
-            if (a.update_pose) {
-                float prev[16], nw[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) prev[i] = ds->pose_c2w[i];
-                pose_mul(prev, aff, nw);
-                store_pose_c2w(ds, nw);
-            }
+            for (int i = 0; i < 16; ++i) { aff[i] = s_aff[i]; prev[i] = ds->pose_c2w[i]; }
+            pose_mul(prev, aff, nw);
+            store_pose_c2w_warp(ds, nw, lane);
         }
     }
     // The frame's result — pose, verdict, counters: the whole state block — goes straight into the host's pinned mirror
     // (zero-copy), followed by a sequence number the host spins on: no D2H copy to enqueue, no stream synchronise to wake
     // up from (the reference: 19 stream syncs + a blocking cudaMemcpy per frame just for ICP).
+#ifdef TFB_ICP_PROFILE
+    if (tid == 0) g_icp_prof[61 * 8 + 1] = clock64();
+#endif
     if (host_state != nullptr) {
         __syncthreads();
         constexpr int WORDS = (int)(sizeof(DevState) / sizeof(unsigned int));
         const unsigned int* src = reinterpret_cast<const unsigned int*>(ds);
         for (int i = tid; i < WORDS; i += ICPA_THREADS) host_state[i] = src[i];
         __syncthreads();
+#ifdef TFB_ICP_PROFILE
+        if (tid == 0) g_icp_prof[61 * 8 + 2] = clock64();
+#endif
         if (tid == 0) {
             __threadfence_system();
             *reinterpret_cast<volatile unsigned int*>(host_state + WORDS) = host_seq;
         }
+#ifdef TFB_ICP_PROFILE
+        if (tid == 0) g_icp_prof[61 * 8 + 3] = clock64();
+#endif
     }
     // the other half of k_set_type3: the allocation counters of the frame start from zero (after the snapshot above, which
     // still reports the previous frame's)
     if (vis != nullptr && ok && tid == 0) { ds->n_claimed = 0; ds->n_new_frame = 0; }
+#ifdef TFB_ICP_PROFILE
+    if (tid == 0) { long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); g_icp_prof[60 * 8 + 3] = gt; }
+#endif
 }
 
 #ifdef TFB_ICP_PROFILE

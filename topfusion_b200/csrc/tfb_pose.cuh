@@ -5,6 +5,7 @@
 // Operation order is identical to the oracle (oracle/tfo_oracle.cpp pose_mul / pose_inv, tfo_kernels_port.cpp
 // mat4_inv); translation units including this header are compiled with --fmad=false.
 #pragma once
+#include <cstddef>
 #include "tfb_common.cuh"
 
 namespace tfb {
@@ -120,6 +121,75 @@ __device__ __forceinline__ void store_pose_c2w(DevState* ds, const float (&c2w)[
         ds->M_w2c[i] = M[i];
         ds->invM_w2c[i] = invM[i];
         ds->M_c2w[i] = Mc[i];
+    }
+}
+
+// pose_inv on a warp: lane j (mod 8) holds column j of the augmented matrix [A | I].  The pivot column is broadcast, every lane
+// swaps, divides and eliminates its own column — per element exactly the operations, in exactly the order, of pose_inv above
+// (one fp64 division and three multiply-subtracts per pivot instead of thirty-two of each in one thread), so the result is the
+// same to the bit.  Every lane returns the whole inverse.  Must be called by all 32 lanes.
+__device__ __forceinline__ void pose_inv_warp(const float (&a)[16], float (&o)[16], int lane) {
+    const int j = lane & 7;
+    double col[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        double v = (i == j - 4) ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (j == k) v = (double)a[i * 4 + k];
+        col[i] = v;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        double cc[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cc[i] = __shfl_sync(0xffffffffu, col[i], c);
+        int piv = c;
+        double best = fabs(cc[c]);
+#pragma unroll
+        for (int r = c + 1; r < 4; ++r) {
+            const double v = fabs(cc[r]);
+            if (v > best) { best = v; piv = r; }
+        }
+#pragma unroll
+        for (int r = c + 1; r < 4; ++r)
+            if (piv == r) {
+                double t = col[c]; col[c] = col[r]; col[r] = t;
+                t = cc[c]; cc[c] = cc[r]; cc[r] = t;
+            }
+        const double d = cc[c];
+        col[c] /= d;
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            if (r != c) col[r] -= cc[r] * col[c];
+    }
+    float f[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) f[i] = (float)col[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[i * 4 + k] = __shfl_sync(0xffffffffu, f[i], 4 + k);
+}
+
+// store_pose_c2w by a whole warp: the inverse spread over the lanes, the 80 words of the state block written 16 at a time
+__device__ __forceinline__ void store_pose_c2w_warp(DevState* ds, const float (&c2w)[16], int lane) {
+    float w2c[16], M[16], invM[16], Mc[16];
+    pose_inv_warp(c2w, w2c, lane);
+    to_colmajor(w2c, M);
+    mat4_inv_cof(M, invM);
+    to_colmajor(c2w, Mc);
+    // the five matrices are the first 80 floats of the state block, in this order: twenty 16-byte stores, one per lane
+    static_assert(offsetof(DevState, pose_c2w) == 0 && offsetof(DevState, pose_w2c) == 64 && offsetof(DevState, M_w2c) == 128 &&
+                  offsetof(DevState, invM_w2c) == 192 && offsetof(DevState, M_c2w) == 256, "layout of the pose block");
+    float4* dst = reinterpret_cast<float4*>(ds);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (lane == q) dst[q] = make_float4(c2w[4 * q], c2w[4 * q + 1], c2w[4 * q + 2], c2w[4 * q + 3]);
+        if (lane == 4 + q) dst[4 + q] = make_float4(w2c[4 * q], w2c[4 * q + 1], w2c[4 * q + 2], w2c[4 * q + 3]);
+        if (lane == 8 + q) dst[8 + q] = make_float4(M[4 * q], M[4 * q + 1], M[4 * q + 2], M[4 * q + 3]);
+        if (lane == 12 + q) dst[12 + q] = make_float4(invM[4 * q], invM[4 * q + 1], invM[4 * q + 2], invM[4 * q + 3]);
+        if (lane == 16 + q) dst[16 + q] = make_float4(Mc[4 * q], Mc[4 * q + 1], Mc[4 * q + 2], Mc[4 * q + 3]);
     }
 }
 
