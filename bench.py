@@ -17,7 +17,9 @@ arms use the same mode.
 Timing: every step is bracketed by two CUDA events on the context's stream; between steps a 256 MB buffer is
 overwritten to evict the 126 MB L2 (outside the timed interval).  `value` feeds frames already resident in HBM;
 `e2e` goes through tfb_process_frame with pinned HOST frames (H2D inside the timed interval) and reads the
-pose/verdict block back every step.
+pose/verdict block back every step.  Both keep the deferred tail (tfb_params.defer_tail = 1), in which every stage of
+one frame's worth of work lies inside one step's bracket; `ingest_from_files` — wall clock around a whole loop from PGM
+files to poses, nothing synchronising with the device between frames — uses the eager tail (defer_tail = 2).
 """
 from __future__ import annotations
 
